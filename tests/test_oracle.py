@@ -1,0 +1,105 @@
+"""Pin the oracle: restatement vs the reference's golden vectors and vs oracle/_ref run live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref, restatement as R
+from ieee_b200.testing import make_retrieval_set, rgbnt201_shaped
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_distance_matches_golden(golden_dir):
+    g = load(golden_dir, "distance_small.npz")
+    a, b = torch.from_numpy(g["a"]), torch.from_numpy(g["b"])
+    # same torch CPU ops in the same order -> identical bits on the same torch build; allow BLAS noise otherwise
+    np.testing.assert_allclose(R.compute_distance_matrix(a, b, "euclidean").numpy(), g["euclidean"], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(R.compute_distance_matrix(a, b, "cosine").numpy(), g["cosine"], rtol=1e-6, atol=1e-6)
+    assert np.all(g["cosine"][:, 3] == 1.0)            # all-zero gallery row (distance.py:77-79, eps clamp)
+    with pytest.raises(ValueError):
+        R.compute_distance_matrix(a, b, "manhattan")
+    with pytest.raises(AssertionError):
+        R.compute_distance_matrix(a, b[:, :5])
+
+
+@pytest.mark.parametrize("name", ["rank_cython_shape.npz", "rank_clustered.npz", "rank_ties_stable.npz"])
+def test_rank_matches_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    cmc, mAP = R.evaluate_rank(g["distmat"], g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"],
+                               max_rank=int(g["max_rank"]))
+    assert cmc.dtype == np.float32 and np.array_equal(cmc, g["cmc"])          # bit-exact CMC
+    assert abs(mAP - float(g["mAP"])) < 1e-12
+    if "cmc_cy" in g:                                                         # Cython path: fp32 accumulators
+        assert np.array_equal(cmc, g["cmc_cy"]) and abs(mAP - float(g["mAP_cy"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["rank_cython_shape.npz", "rank_clustered.npz", "rank_ties_stable.npz"])
+def test_counting_form_equals_sort_form(golden_dir, name):
+    """positions by counting give the same CMC / mAP as the sort."""
+    g = load(golden_dir, name)
+    pos = R.kept_positions(g["distmat"], g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"])
+    cmc, mAP, nv = R.metrics_from_positions(pos, int(g["max_rank"]), g["distmat"].shape[1])
+    assert np.array_equal(cmc, g["cmc"]) and abs(mAP - float(g["mAP"])) < 1e-12
+
+
+def test_rerank_matches_golden(golden_dir):
+    g = load(golden_dir, "rerank_small.npz")
+    for key, kw in (("out_default", {}), ("out_small", dict(k1=6, k2=3, lambda_value=0.5)),
+                    ("out_k2_1", dict(k1=8, k2=1, lambda_value=0.3))):
+        out = R.re_ranking(g["qg"], g["qq"], g["gg"], **kw)
+        assert out.dtype == np.float32 and out.shape == g[key].shape
+        assert np.array_equal(out, g[key]), key                               # same NumPy ops -> same bits
+
+
+@needs_ref
+def test_restatement_vs_compiled_reference_live():
+    s = make_retrieval_set(120, 900, 40, 5, dim=256, sigma=2.5, seed=21, distractor_frac=0.1)
+    d_ref = ref.compute_distance_matrix(s.qf, s.gf, "euclidean").numpy()
+    d_mine = R.compute_distance_matrix(s.qf, s.gf, "euclidean").numpy()
+    np.testing.assert_allclose(d_mine, d_ref, rtol=1e-6, atol=1e-4)
+    for metric in ("euclidean", "cosine"):
+        d = ref.compute_distance_matrix(s.qf, s.gf, metric).numpy()
+        ties = R.count_row_ties(d)
+        cmc_ref, map_ref = ref.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, max_rank=10)
+        cmc, mAP = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, max_rank=10, stable=(ties > 0))
+        if ties == 0:
+            assert np.array_equal(cmc, cmc_ref) and abs(mAP - map_ref) < 1e-12
+        else:   # the reference's own order on ties is undefined; metrics may move by a few ties' worth
+            assert np.abs(cmc - cmc_ref).max() <= ties / len(s.q_pids) and abs(mAP - map_ref) < 1e-3
+        cmc_cy, map_cy = ref.evaluate_cy(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, 10)
+        assert np.abs(cmc - cmc_cy).max() <= ties / len(s.q_pids) and abs(mAP - map_cy) < 1e-3
+
+
+@needs_ref
+def test_rerank_restatement_vs_compiled_reference_live():
+    s = make_retrieval_set(30, 90, 10, 3, dim=64, sigma=2.0, seed=4)
+    qg = ref.compute_distance_matrix(s.qf, s.gf).numpy()
+    qq = ref.compute_distance_matrix(s.qf, s.qf).numpy()
+    gg = ref.compute_distance_matrix(s.gf, s.gf).numpy()
+    mine = R.re_ranking(qg, qq, gg, stable=False)
+    theirs = ref.re_ranking(qg, qq, gg)
+    assert np.array_equal(mine, theirs)
+
+
+def test_rgbnt201_shape_has_natural_ties():
+    """Query set == gallery set (RGBNT201.py:33-34): fp32 distances collide, so the tie rule matters."""
+    s = rgbnt201_shaped()
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    assert d.shape == (836, 836)
+    assert (np.diag(d) < d.mean() * 1e-3).all()        # self-distance ~ 0 (squared, unclamped, F7)
+    cmc, mAP = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert 0.2 < mAP < 0.8 and cmc.shape == (20,)
+
+
+def test_invalid_queries_and_errors():
+    d = np.random.RandomState(0).rand(4, 30).astype(np.float32)
+    with pytest.raises(AssertionError):
+        R.evaluate_rank(d, np.arange(4) + 100, np.arange(30), np.zeros(4, int), np.ones(30, int))
+    with pytest.raises(TypeError):
+        R.evaluate_rank(d, np.arange(4), np.arange(30), np.zeros(4, int), np.ones(30, int), use_metric_cuhk03=True)
