@@ -1,0 +1,100 @@
+"""ctypes binding of libieee_b200.so (include/ieee_b200.h).  No CPU fallback: a missing library or a
+missing CUDA device raises, it never silently computes on the host."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libieee_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_VALID_QUERY, ERR_SHORT_RANK_LIST, ERR_CAPACITY = range(7)
+METRICS = {"euclidean": 0, "cosine": 1}
+PRECISIONS = {"bf16x3": 0, "bf16": 1, "fp32_simt": 2}
+DTYPES = {torch.float32: 0, torch.bfloat16: 1}
+
+i64, i32, sz, vp, f32 = C.c_int64, C.c_int32, C.c_size_t, C.c_void_p, C.c_float
+
+
+class EvalSummary(C.Structure):
+    _fields_ = [("mAP", C.c_double), ("sum_ap", C.c_double), ("num_valid", i64), ("num_ties", i64),
+                ("num_short", i64), ("max_rank", i32), ("status", i32), ("reserved", i64 * 2)]
+
+
+# name -> (restype, argtypes); must list every symbol include/ieee_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "ieee_last_error": (C.c_char_p, []),
+    "ieee_abi_version": (C.c_int, []),
+    "ieee_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ieee_set_cta_group": (C.c_int, [C.c_int]),
+    "ieee_launch_count": (i64, []),
+    "ieee_packed_bytes": (sz, [i64, i64, C.c_int]),
+    "ieee_pack_features": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "ieee_distmat_packed": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp]),
+    "ieee_distmat_workspace_bytes": (sz, [i64, i64, i64, C.c_int]),
+    "ieee_distmat": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, i64, vp, sz, vp]),
+    "ieee_gallery_group_bytes": (sz, [i64]),
+    "ieee_gallery_group": (C.c_int, [vp, i64, vp, vp]),
+    "ieee_rank_list_cap_sync": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(i32), vp]),
+    "ieee_rank_gather": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
+    "ieee_rank_count_smem_bytes": (sz, [i32, i32]),
+    "ieee_rank_count": (C.c_int, [vp, i64, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "ieee_rank_query_metrics": (C.c_int, [vp, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp]),
+    "ieee_rank_reduce": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "ieee_rank_finalize_workspace_bytes": (sz, [i64]),
+    "ieee_rank_finalize": (C.c_int, [vp, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "ieee_eval_workspace_bytes": (sz, [i64, i64, i32]),
+    "ieee_eval_market1501": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
+    "ieee_topk": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "ieee_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
+    "ieee_rerank_workspace_bytes": (sz, [i64, i64, i32, i32]),
+    "ieee_rerank": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, f32, vp, i64, vp, sz, vp]),
+}
+
+_lib = None
+
+
+class IeeeB200Error(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"libieee_b200 error {code}: {text}")
+        self.code = code
+        self.text = text
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed just to load and inspect symbols)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m ieee_b200.build` "
+                               "(nvcc, sm_100a). ieee_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != OK:
+        raise IeeeB200Error(code, load().ieee_last_error().decode())
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("ieee_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args))

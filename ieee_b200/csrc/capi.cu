@@ -1,0 +1,327 @@
+// extern "C" surface of libieee_b200.so (see include/ieee_b200.h).
+#include <atomic>
+
+#include "common.cuh"
+
+namespace ieee {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_error; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// implemented in the other translation units
+int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
+                  void* packed, cudaStream_t stream);
+int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group);
+int distmat_simt(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, float* out,
+                 int64_t ldo, cudaStream_t stream);
+size_t gallery_group_bytes(int64_t G);
+int gallery_group(const int64_t* g_pids, int64_t G, void* blob, cudaStream_t stream);
+int rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* cap_dev, cudaStream_t stream);
+int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel, int32_t* n_rel,
+                uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream);
+size_t rank_count_smem(int shards, int cap);
+int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
+               const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
+               int32_t* counts, unsigned long long* ties, cudaStream_t stream);
+size_t rank_finalize_workspace_bytes(int64_t Q);
+int rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+                       int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, cudaStream_t stream);
+int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
+                const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, cudaStream_t stream);
+int rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+                  int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
+                  double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream);
+int topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
+         const int64_t* q_camids, const int64_t* g_pids, const int64_t* g_camids, int32_t k, int32_t* idx, float* val,
+         cudaStream_t stream);
+int topk_merge(const int32_t* idx_all, const float* val_all, int32_t shards, int64_t Q, int32_t k, int32_t* idx, float* val,
+               cudaStream_t stream);
+size_t rerank_workspace_bytes(int64_t Q, int64_t G, int32_t k1, int32_t k2);
+int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, const float* g_g, int64_t ld_gg, int64_t Q,
+           int64_t G, int32_t k1, int32_t k2, float lambda_value, float* out, int64_t ldo, void* workspace,
+           size_t workspace_bytes, cudaStream_t stream);
+
+static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default pairing of the tensor-core kernel
+static int cta_group_default() {
+  if (g_cta_group < 0) {
+    const char* e = getenv("IEEE_B200_CTA_GROUP");
+    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_cta_group;
+}
+
+static int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (libieee_b200 has no CPU fallback)");
+    return IEEE_ERR_CUDA;
+  }
+  return IEEE_OK;
+}
+
+// bump allocator over a caller-provided workspace
+struct Arena {
+  uint8_t* base;
+  size_t size, off;
+  void* take(size_t bytes) {
+    size_t o = align256(off);
+    if (o + bytes > size) return nullptr;
+    off = o + bytes;
+    return base + o;
+  }
+};
+
+}  // namespace ieee
+
+using namespace ieee;
+
+extern "C" {
+
+const char* ieee_last_error(void) { return get_error(); }
+int ieee_abi_version(void) { return IEEE_B200_ABI_VERSION; }
+
+int ieee_device_info(int* sm, int* cc) {
+  int rc = check_device();
+  if (rc) return rc;
+  int dev = 0, major = 0, minor = 0;
+  IEEE_CUDA_CHECK(cudaGetDevice(&dev));
+  IEEE_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  IEEE_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = sm_count();
+  if (cc) *cc = major * 10 + minor;
+  return IEEE_OK;
+}
+
+int64_t ieee_launch_count(void) { return g_launches.load(); }
+
+int ieee_set_cta_group(int cg) {
+  const int prev = cta_group_default();
+  if (cg == 1 || cg == 2) g_cta_group = cg;
+  return prev;
+}
+
+// ---- distance ------------------------------------------------------------------------------------------
+size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision) {
+  if (rows < 0 || D <= 0) return 0;
+  return packed_layout(rows, D, precision).total;
+}
+
+int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,
+                       int precision, void* packed, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return pack_features(x, dtype, ld, rows, D, metric, normalize, precision, packed, (cudaStream_t)stream);
+}
+
+int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                        int precision, float* out, int64_t ldo, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(q_packed && g_packed && out, "distmat: null pointer");
+  IEEE_REQUIRE(Q >= 0 && G >= 0 && D > 0 && ldo >= G, "distmat: bad shape Q=%lld G=%lld D=%lld ldo=%lld", (long long)Q,
+               (long long)G, (long long)D, (long long)ldo);
+  IEEE_REQUIRE(Q < (int64_t(1) << 31) && G < (int64_t(1) << 31), "distmat: Q and G must fit int32");
+  IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
+  if (Q == 0 || G == 0) return IEEE_OK;
+  if (precision == IEEE_PREC_FP32_SIMT) return distmat_simt(q_packed, Q, g_packed, G, D, metric, out, ldo, (cudaStream_t)stream);
+  IEEE_REQUIRE(precision == IEEE_PREC_BF16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
+  return distmat_umma(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, (cudaStream_t)stream, cta_group_default());
+}
+
+size_t ieee_distmat_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision) {
+  return ieee_packed_bytes(Q, D, precision) + ieee_packed_bytes(G, D, precision) + 512;
+}
+
+int ieee_distmat(const void* q, const void* g, int dtype, int64_t ldq, int64_t ldg, int64_t Q, int64_t G, int64_t D,
+                 int metric, int normalize, int precision, float* out, int64_t ldo, void* workspace, size_t workspace_bytes,
+                 ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "distmat: workspace must be 256-byte aligned");
+  if (workspace_bytes < ieee_distmat_workspace_bytes(Q, G, D, precision)) {
+    set_error("distmat: workspace too small (%zu < %zu)", workspace_bytes, ieee_distmat_workspace_bytes(Q, G, D, precision));
+    return IEEE_ERR_WORKSPACE;
+  }
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  void* qp = w;
+  void* gp = w + align256(ieee_packed_bytes(Q, D, precision));
+  if ((rc = ieee_pack_features(q, dtype, ldq, Q, D, metric, normalize, precision, qp, stream))) return rc;
+  if ((rc = ieee_pack_features(g, dtype, ldg, G, D, metric, normalize, precision, gp, stream))) return rc;
+  return ieee_distmat_packed(qp, Q, gp, G, D, metric, precision, out, ldo, stream);
+}
+
+// ---- ranking -------------------------------------------------------------------------------------------
+size_t ieee_gallery_group_bytes(int64_t G) { return G > 0 ? gallery_group_bytes(G) : 0; }
+
+int ieee_gallery_group(const int64_t* g_pids, int64_t G, void* group, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return gallery_group(g_pids, G, group, (cudaStream_t)stream);
+}
+
+int ieee_rank_list_cap_sync(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* scratch_dev,
+                            int32_t* cap_host, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(group && q_pids && scratch_dev && cap_host, "rank_list_cap: null pointer");
+  if ((rc = rank_list_cap(group, G, q_pids, Q, scratch_dev, (cudaStream_t)stream))) return rc;
+  IEEE_CUDA_CHECK(cudaMemcpyAsync(cap_host, scratch_dev, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  IEEE_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return IEEE_OK;
+}
+
+int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                     const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel,
+                     int32_t* n_rel, uint64_t* junk, int32_t* n_junk, int32_t* overflow_flag, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, g_offset, cap, rel, n_rel, junk, n_junk,
+                     overflow_flag, (cudaStream_t)stream);
+}
+
+size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap) { return rank_count_smem(shards, cap); }
+
+int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards, int32_t cap,
+                    const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
+                    int32_t* counts, unsigned long long* ties, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rank_count(distmat, ld, Q, G, g_offset, shards, cap, rel_all, n_rel_all, junk, n_junk, counts, ties,
+                    (cudaStream_t)stream);
+}
+
+int ieee_rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+                            int32_t cap, int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
+                            ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rank_query_metrics(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ap, first, short_list, (cudaStream_t)stream);
+}
+
+int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
+                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rank_reduce(ap, first, short_list, Q, max_rank, ties, cmc, summary, (cudaStream_t)stream);
+}
+
+size_t ieee_rank_finalize_workspace_bytes(int64_t Q) { return Q > 0 ? rank_finalize_workspace_bytes(Q) : 0; }
+
+int ieee_rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+                       int32_t cap, int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
+                       double* per_query_ap, int32_t* per_query_first, void* workspace, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rank_finalize(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ties, cmc, summary, per_query_ap,
+                       per_query_first, workspace, (cudaStream_t)stream);
+}
+
+// workspace of the one-shot evaluate: group | cap scratch | rel | junk | n_rel | n_junk | counts | ties | finalize ws
+size_t ieee_eval_workspace_bytes(int64_t Q, int64_t G, int32_t cap) {
+  if (Q <= 0 || G <= 0) return 0;
+  if (cap <= 0) cap = (int32_t)(G < 4096 ? G : 4096);
+  size_t b = 0;
+  b += align256(gallery_group_bytes(G));
+  b += 256;                                        // cap scratch + overflow flag + ties
+  b += 2 * align256(size_t(Q) * cap * 8);          // rel, junk
+  b += 2 * align256(size_t(Q) * 4);                // n_rel, n_junk
+  b += align256(size_t(Q) * (cap + 1) * 4);        // counts
+  b += align256(rank_finalize_workspace_bytes(Q));
+  return b + 256;
+}
+
+int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
+                         const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
+                         int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
+                         ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(distmat && q_pids && g_pids && q_camids && g_camids && cmc && summary && workspace, "eval: null pointer");
+  IEEE_REQUIRE(Q > 0 && G > 0 && ld >= G && max_rank >= 1, "eval: bad shape Q=%lld G=%lld ld=%lld max_rank=%d", (long long)Q,
+               (long long)G, (long long)ld, max_rank);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "eval: workspace must be 256-byte aligned");
+  Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
+  void* group = a.take(gallery_group_bytes(G));
+  int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
+  if (!group || !scratch) { set_error("eval: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  if ((rc = gallery_group(g_pids, G, group, stream))) return rc;
+  int32_t need = 0;
+  if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
+  if (need < 1) need = 1;
+  if (cap <= 0) cap = need;
+  if (need > cap) {
+    set_error("eval: a query has %d same-identity gallery items but list capacity is %d", need, cap);
+    return IEEE_ERR_CAPACITY;
+  }
+  cap = need;   // tight lists: less shared memory in the count kernel
+  uint64_t* rel = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
+  uint64_t* junk = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
+  int32_t* n_rel = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  int32_t* n_junk = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  int32_t* counts = static_cast<int32_t*>(a.take(size_t(Q) * (cap + 1) * 4));
+  void* fws = a.take(rank_finalize_workspace_bytes(Q));
+  if (!rel || !junk || !n_rel || !n_junk || !counts || !fws) {
+    set_error("eval: workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
+              ieee_eval_workspace_bytes(Q, G, cap), cap);
+    return IEEE_ERR_WORKSPACE;
+  }
+  IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
+  unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
+  if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
+  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
+  return rank_finalize(counts, n_rel, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
+}
+
+int ieee_topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
+              const int64_t* q_camids, const int64_t* g_pids, const int64_t* g_camids, int32_t k, int32_t* idx, float* val,
+              ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return topk(distmat, ld, Q, G, g_offset, q_pids, q_camids, g_pids, g_camids, k, idx, val, (cudaStream_t)stream);
+}
+
+int ieee_topk_merge(const int32_t* idx_all, const float* val_all, int32_t shards, int64_t Q, int32_t k, int32_t* idx,
+                    float* val, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return topk_merge(idx_all, val_all, shards, Q, k, idx, val, (cudaStream_t)stream);
+}
+
+size_t ieee_rerank_workspace_bytes(int64_t Q, int64_t G, int32_t k1, int32_t k2) { return rerank_workspace_bytes(Q, G, k1, k2); }
+
+int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, const float* g_g, int64_t ld_gg, int64_t Q,
+                int64_t G, int32_t k1, int32_t k2, float lambda_value, float* out, int64_t ldo, void* workspace,
+                size_t workspace_bytes, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return rerank(q_g, ld_qg, q_q, ld_qq, g_g, ld_gg, Q, G, k1, k2, lambda_value, out, ldo, workspace, workspace_bytes,
+                (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// Distance-matrix contraction on the sm_100a tensor cores.
+//
+// Replaces torchreid/metrics/distance.py:59-64 (out = (|a|^2 + |b|^2) - 2 a b^T via addmm_) and
+// distance.py:77-80 (out = 1 - normalize(a) normalize(b)^T via mm).  Both feature matrices are row-major
+// [rows, D], i.e. K-major operands of C = A * B^T -- the layout tcgen05.mma consumes directly.
+//
+// Kernel shape (persistent, warp specialised, one CTA per SM):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) into a kStages smem ring
+//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (kind::f16, bf16 in, fp32 accumulate in TMEM)
+//   warp 2   : TMEM allocator -- 512 columns = two 128 x 256 fp32 accumulator stages
+//   warps 4-7: epilogue       -- tcgen05.ld -> registers -> smem transpose -> coalesced global stores of
+//                                d = fma(alpha, acc, rq[row] + rg[col])
+// kCtaGroup == 2 pairs two SMs on one 256 x 256 tile (tcgen05.mma.cta_group::2): each CTA loads its own 128
+// rows of A and HALF of the B tile, so per-SM shared-memory and L2 traffic per flop halves.
+//
+// BF16X3 (fp32-equivalent) mode runs three k-passes per 64-wide k block into the same accumulator:
+// (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ieee {
+
+constexpr int BLOCK_M = 128;  // rows of A per CTA == TMEM lanes
+constexpr int BLOCK_N = 256;  // columns per tile == UMMA N
+constexpr int BLOCK_K = 64;   // bf16 elements per k block == one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kEpilogueWarps = 4;
+constexpr int kThreads = 128 + 32 * kEpilogueWarps;
+constexpr int kStagePitch = 33;  // floats; padded 32 x 32 transpose tile per epilogue warp
+
+template <int CG>
+struct GemmCfg {
+  static constexpr int kStages = (CG == 1) ? 4 : 6;
+  static constexpr int kBRows = BLOCK_N / CG;                      // B rows this CTA loads
+  static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
+  static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;        // 32 KB / 16 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kEpiBytes = kEpilogueWarps * 32 * kStagePitch * 4;
+  static constexpr uint32_t kBarBytes = 256;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /* alignment slack */;
+};
+
+struct GemmParams {
+  const float* rq;   // per query row term (euclidean: squared norm; cosine: nullptr -> 1)
+  const float* rg;   // per gallery row term (euclidean: squared norm; cosine: nullptr -> 0)
+  float* out;
+  int64_t ldo;
+  int Q, G;
+  int num_kb;        // Dp / 64
+  int nseg;          // 1 (BF16) or 3 (BF16X3)
+  float alpha;       // -2 (euclidean) or -1 (cosine)
+  int num_m_tiles, num_n_tiles;
+};
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<CG>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  float* smem_epi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA   (lives in the pair leader for CG == 2)
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA   (per CTA)
+  uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue (per CTA)
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]    epilogue -> MMA (leader)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
+  const bool is_leader = cta_rank == 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_b_hi);
+    if (p.nseg == 3) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], CG);   // one arrive(+expect_tx) per producing CTA
+      mbar_init(&empty_bar[i], 1);   // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], CG * kEpilogueWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // Persistent tile loop shared by all roles: tile t -> (m fastest, so co-resident CTAs share B tiles in L2).
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int group_id = blockIdx.x / CG;
+  const int num_groups = gridDim.x / CG;
+  const int total_kb = p.num_kb * p.nseg;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = group_id; t < num_tiles; t += num_groups) {
+        const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+        const int row_a = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+        const int row_b = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int kk = kb / p.nseg, seg = kb - kk * p.nseg;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const CUtensorMap* ma = (seg == 2) ? &tm_a_lo : &tm_a_hi;
+          const CUtensorMap* mb = (seg == 1) ? &tm_b_lo : &tm_b_hi;
+          void* sa = smem_a + stage * Cfg::kABytes;
+          void* sb = smem_b + stage * Cfg::kBBytes;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+            tma_load_2d(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+          } else {
+            // Both CTAs' bytes are counted on the leader's barrier; each CTA contributes one arrival.
+            if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+            tma_load_2d_pair(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+            if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair leader only) =====================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = group_id; t < num_tiles; t += num_groups, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit<CG>(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == total_kb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                       // == warp % 4 -> TMEM lane quarter
+    float* stage_buf = smem_epi + ew * 32 * kStagePitch;
+    int it = 0;
+    for (int t = group_id; t < num_tiles; t += num_groups, ++it) {
+      const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + ew * 32;   // first row of this warp
+      const int col_tile = n_blk * BLOCK_N;
+      // lane l keeps the row term of row0 + l; broadcast by shuffle in the store loop
+      float rq_lane = 1.0f;
+      if (p.rq != nullptr) rq_lane = (row0 + lane < p.Q) ? p.rq[row0 + lane] : 0.0f;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (uint32_t(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {
+          // all of this thread's accumulator reads are done: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        const int col = col_tile + c * 32 + lane;
+        float rg_lane = 0.0f;
+        if (p.rg != nullptr && col < p.G) rg_lane = p.rg[col];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage_buf[lane * kStagePitch + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        if (col_tile + c * 32 < p.G) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float rq = __shfl_sync(0xffffffffu, rq_lane, r);
+            const float a = stage_buf[r * kStagePitch + lane];
+            const int row = row0 + r;
+            if (row < p.Q && col < p.G)
+              p.out[(int64_t)row * p.ldo + col] = __fmaf_rn(p.alpha, a, __fadd_rn(rq, rg_lane));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// bf16 plane [rows, Dp] row-major -> tiles of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds.
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t Dp, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return IEEE_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld Dp=%lld)", (int)r, (long long)rows, (long long)Dp);
+    return IEEE_ERR_CUDA;
+  }
+  return IEEE_OK;
+}
+
+template <int CG>
+static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                       int precision, float* out, int64_t ldo, cudaStream_t stream) {
+  using Cfg = GemmCfg<CG>;
+  PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
+  const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
+  const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tmap(&ta_hi, qb + lq.hi_off, Q, lq.Dp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tb_hi, gb + lg.hi_off, G, lg.Dp, Cfg::kBRows))) return rc;
+  if (precision == IEEE_PREC_BF16X3) {
+    if ((rc = make_tmap(&ta_lo, qb + lq.lo_off, Q, lq.Dp, BLOCK_M))) return rc;
+    if ((rc = make_tmap(&tb_lo, gb + lg.lo_off, G, lg.Dp, Cfg::kBRows))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  GemmParams p;
+  const bool euclid = metric == IEEE_METRIC_EUCLIDEAN;
+  p.rq = euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr;
+  p.rg = euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr;
+  p.alpha = euclid ? -2.0f : -1.0f;
+  p.out = out;
+  p.ldo = ldo;
+  p.Q = (int)Q;
+  p.G = (int)G;
+  p.num_kb = (int)(lq.Dp / BLOCK_K);
+  p.nseg = precision == IEEE_PREC_BF16X3 ? 3 : 1;
+  p.num_m_tiles = (int)((Q + BLOCK_M * CG - 1) / (BLOCK_M * CG));
+  p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int groups = sm_count() / CG;
+  if (groups > num_tiles) groups = num_tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  count_launch();
+  return IEEE_OK;
+}
+
+int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group) {
+  if (cta_group == 2)
+    return launch_umma<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);
+  return launch_umma<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);
+}
+
+}  // namespace ieee

@@ -1,0 +1,142 @@
+// Feature packing: fp32 / bf16 rows -> the operand planes the contraction kernels read.
+//
+// Covers torchreid/engine/engine.py:391-394 (optional F.normalize of both sets), the row-norm terms of
+// torchreid/metrics/distance.py:59-61 (pow(2).sum(1)) and the F.normalize calls of distance.py:77-78
+// (x / max(||x||_2, 1e-12)), fused with the fp32 -> bf16 hi/lo split the tensor-core kernel needs.
+#include "common.cuh"
+
+namespace ieee {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int VEC>
+struct RowLoader;
+template <>
+struct RowLoader<float, 4> {
+  __device__ static void load(const float* p, int64_t i, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct RowLoader<float, 1> {
+  __device__ static void load(const float* p, int64_t i, float (&v)[1]) { v[0] = __ldg(p + i); }
+};
+template <>
+struct RowLoader<__nv_bfloat16, 1> {
+  __device__ static void load(const __nv_bfloat16* p, int64_t i, float (&v)[1]) { v[0] = __bfloat162float(p[i]); }
+};
+
+enum PackMode { PACK_BF16 = 0, PACK_BF16_HILO = 1, PACK_F32 = 2 };
+
+// One warp per row.  n_norm = how many times the row is L2-normalised before the metric sees it: engine
+// normalize_feature (engine.py:391-394) and/or cosine's own F.normalize (distance.py:77-78).  Normalising twice
+// is not the identity in fp32, so the reference's sequence of divisions is reproduced, not collapsed.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
+                                                         int n_norm, int mode, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, float* __restrict__ f32,
+                                                         float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * ld;
+  float den[2] = {1.0f, 1.0f};
+  for (int pass = 0; pass < n_norm; ++pass) {
+    float s = 0.f;
+    for (int i = lane * VEC; i < D; i += 32 * VEC) {
+      float v[VEC];
+      RowLoader<T, VEC>::load(xr, i, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float t = v[j];
+        if (pass == 1) t = __fdiv_rn(t, den[0]);
+        s = __fmaf_rn(t, t, s);
+      }
+    }
+    s = warp_sum(s);
+    den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);  // F.normalize: clamp_min(norm, eps)
+  }
+  float sq = 0.f;
+  for (int i = lane * VEC; i < Dp; i += 32 * VEC) {
+    float v[VEC];
+    if (i < D) {
+      RowLoader<T, VEC>::load(xr, i, v);  // D % VEC == 0 on the vector path
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = 0.f;
+    }
+    __nv_bfloat16 h[VEC], l[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float t = v[j];
+      if (n_norm >= 1) t = __fdiv_rn(t, den[0]);
+      if (n_norm >= 2) t = __fdiv_rn(t, den[1]);
+      h[j] = __float2bfloat16_rn(t);
+      const float hf = __bfloat162float(h[j]);
+      l[j] = __float2bfloat16_rn(t - hf);
+      // the row term must describe the numbers the contraction actually multiplies
+      const float u = (mode == PACK_BF16) ? hf : t;
+      sq = __fmaf_rn(u, u, sq);
+      v[j] = t;
+    }
+    const int64_t o = row * (int64_t)Dp + i;
+    if (mode == PACK_F32) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) f32[o + j] = v[j];
+    } else {
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
+        if (mode == PACK_BF16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
+      } else {
+        hi[o] = h[0];
+        if (mode == PACK_BF16_HILO) lo[o] = l[0];
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) norms[row] = sq;
+}
+
+int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
+                  void* packed, cudaStream_t stream) {
+  IEEE_REQUIRE(x != nullptr && packed != nullptr, "pack_features: null pointer");
+  IEEE_REQUIRE(rows >= 0 && D > 0 && ld >= D, "pack_features: bad shape rows=%lld D=%lld ld=%lld", (long long)rows,
+               (long long)D, (long long)ld);
+  IEEE_REQUIRE(D <= (1 << 24), "pack_features: feature dim too large");
+  IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "pack_features: unknown dtype %d", dtype);
+  IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
+  IEEE_REQUIRE(precision >= IEEE_PREC_BF16X3 && precision <= IEEE_PREC_FP32_SIMT, "unknown precision %d", precision);
+  if (rows == 0) return IEEE_OK;
+  PackedLayout L = packed_layout(rows, D, precision);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 255) == 0, "pack_features: packed buffer must be 256-byte aligned");
+  auto* hi = reinterpret_cast<__nv_bfloat16*>(base + L.hi_off);
+  auto* lo = reinterpret_cast<__nv_bfloat16*>(base + L.lo_off);
+  auto* f32 = reinterpret_cast<float*>(base);
+  auto* norms = reinterpret_cast<float*>(base + L.norm_off);
+  const int n_norm = (normalize ? 1 : 0) + (metric == IEEE_METRIC_COSINE ? 1 : 0);
+  const int mode = precision == IEEE_PREC_FP32_SIMT ? PACK_F32 : (precision == IEEE_PREC_BF16X3 ? PACK_BF16_HILO : PACK_BF16);
+  const int warps = 8;
+  dim3 grid((unsigned)((rows + warps - 1) / warps)), block(warps * 32);
+  if (dtype == IEEE_DTYPE_F32) {
+    const float* xf = static_cast<const float*>(x);
+    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xf) & 15) == 0);
+    if (vec)
+      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+    else
+      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+  } else {
+    pack_rows_kernel<__nv_bfloat16, 1><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, (int)D,
+                                                                   (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+  }
+  count_launch();
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
+}  // namespace ieee

@@ -1,0 +1,192 @@
+"""Device-resident evaluation: the reference's ``Engine._evaluate`` tail (torchreid/engine/engine.py:391-425)
+without its host round trips.
+
+The reference concatenates features on the CPU (engine.py:368-373), normalises (:391-394), builds the whole
+Q x G matrix with torch CPU (:399-400), optionally re-ranks (:402-406) and calls ``evaluate_rank`` (:410-417).
+Here features stay in HBM, the gallery is packed and grouped once, queries are processed in blocks whose
+distance block lives only in HBM scratch, and -- when the process group has more than one rank -- every rank
+owns a contiguous slice of the gallery: relevant-pair distances are all-gathered, integer rank counts are
+all-reduced, and every rank ends with the same (cmc, mAP) the single-GPU path produces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .metrics.rank import GalleryLabels, RankStages, _as_device, raise_for_status
+from .utils.rerank import re_ranking_device
+
+DEFAULT_BLOCK_BYTES = 4 << 30   # HBM scratch for one distance block
+
+
+def shard_bounds(num_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous gallery slice of ``rank``: [start, stop).  Global index = local index + start, so the
+    (distance, index) tie order is the same as on one GPU."""
+    base, rem = divmod(num_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class PackedFeatures:
+    """Feature rows in the operand layout of the tensor-core kernel (ieee_pack_features)."""
+
+    def __init__(self, feats: torch.Tensor, metric: str, normalize: bool, precision: str):
+        assert feats.is_cuda and feats.dim() == 2 and feats.dtype in _lib.DTYPES
+        if feats.stride(1) != 1:
+            feats = feats.contiguous()
+        self.rows, self.D = feats.shape
+        self.metric, self.precision = _lib.METRICS[metric], _lib.PRECISIONS[precision]
+        lib = _lib.load()
+        self.buf = torch.empty(max(lib.ieee_packed_bytes(self.rows, self.D, self.precision), 256), dtype=torch.uint8,
+                               device=feats.device)
+        if self.rows:
+            _lib.call("ieee_pack_features", feats.data_ptr(), _lib.DTYPES[feats.dtype], feats.stride(0), self.rows, self.D,
+                      self.metric, int(normalize), self.precision, self.buf.data_ptr(), _lib.stream())
+
+
+def packed_distmat(q: PackedFeatures, g: PackedFeatures, out: torch.Tensor) -> torch.Tensor:
+    assert q.D == g.D and q.metric == g.metric and q.precision == g.precision
+    _lib.call("ieee_distmat_packed", q.buf.data_ptr(), q.rows, g.buf.data_ptr(), g.rows, q.D, q.metric, q.precision,
+              out.data_ptr(), out.stride(0), _lib.stream())
+    return out
+
+
+class RetrievalEvaluator:
+    """distmat -> rank -> CMC/mAP over a (possibly sharded) gallery.
+
+    ``gf, g_pids, g_camids`` are THIS rank's gallery slice (the whole gallery when ``group`` is None);
+    ``g_offset`` its first global row and ``g_total`` the gallery size over all ranks.
+    """
+
+    def __init__(self, gf: torch.Tensor, g_pids, g_camids, dist_metric: str = "euclidean", normalize_feature: bool = False,
+                 precision: str | None = None, max_rank: int = 20, group=None, g_offset: int = 0, g_total: int | None = None,
+                 block_bytes: int = DEFAULT_BLOCK_BYTES):
+        _lib.require_cuda()
+        if dist_metric not in _lib.METRICS:
+            raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(dist_metric))
+        self.device = gf.device
+        self.metric, self.normalize = dist_metric, normalize_feature
+        self.precision = precision or ("bf16" if gf.dtype == torch.bfloat16 else "bf16x3")
+        self.max_rank = max_rank
+        self.group = group
+        self.world = 1 if group is None else torch.distributed.get_world_size(group)
+        self.g_offset = g_offset
+        self.block_bytes = block_bytes
+        with torch.cuda.device(self.device):
+            self.gallery = PackedFeatures(gf, dist_metric, normalize_feature, self.precision)
+            self.labels = GalleryLabels(g_pids, g_camids, self.device)
+        self.G = self.gallery.rows
+        self.g_total = self.G if g_total is None else g_total
+        self._block = None
+
+    # -- one query block ---------------------------------------------------------------------------------
+    def _block_rows(self, Q: int) -> int:
+        rows = max(128, int(self.block_bytes // (4 * max(self.G, 1))) // 128 * 128)
+        return min(Q, rows)
+
+    def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties):
+        Qb = dist.shape[0]
+        st = RankStages(Qb, cap, self.world, self.device)
+        st.gather(dist, qp, qc, self.labels, self.g_offset)
+        if self.world > 1:
+            import torch.distributed as dist_
+            rel_all = torch.empty((self.world, Qb, cap), dtype=torch.int64, device=self.device)
+            n_rel_all = torch.empty((self.world, Qb), dtype=torch.int32, device=self.device)
+            dist_.all_gather_into_tensor(rel_all, st.rel, group=self.group)
+            dist_.all_gather_into_tensor(n_rel_all, st.n_rel, group=self.group)
+            st.count(dist, self.G, self.g_offset, rel_all, n_rel_all)
+            dist_.all_reduce(st.counts, group=self.group)
+        else:
+            n_rel_all = st.n_rel
+            st.count(dist, self.G, self.g_offset)
+        ties += st.flags[1:2]
+        _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), n_rel_all.data_ptr(), Qb, self.g_total, self.world, cap,
+                  self.max_rank, ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
+        return st
+
+    def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False):
+        """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank."""
+        with torch.cuda.device(self.device):
+            Q = qf.shape[0]
+            qp = _as_device(q_pids, torch.int64, self.device)
+            qc = _as_device(q_camids, torch.int64, self.device)
+            cap = self.labels.list_cap(qp)
+            if self.world > 1:
+                import torch.distributed as dist_
+                cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
+                dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
+                cap = int(cap_t.item())
+            ap = torch.empty(Q, dtype=torch.float64, device=self.device)
+            first = torch.empty(Q, dtype=torch.int32, device=self.device)
+            short = torch.empty(Q, dtype=torch.int32, device=self.device)
+            ties = torch.zeros(1, dtype=torch.int64, device=self.device)
+            rows = self._block_rows(Q)
+            if self._block is None or self._block.shape[0] < rows:
+                self._block = torch.empty((rows, self.G), dtype=torch.float32, device=self.device)
+            full = None
+            for s in range(0, Q, rows):
+                e = min(Q, s + rows)
+                qpk = PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
+                dist = packed_distmat(qpk, self.gallery, self._block[: e - s])
+                self._rank_block(dist, qp[s:e], qc[s:e], cap, ap[s:e], first[s:e], short[s:e], ties)
+                if return_distmat:
+                    full = dist.clone() if full is None else torch.cat([full, dist], 0)
+            if self.world > 1:
+                import torch.distributed as dist_
+                dist_.all_reduce(ties, group=self.group)
+            k_eff = min(self.max_rank, self.g_total)
+            cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
+            summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
+            _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
+                      cmc.data_ptr(), summ.data_ptr(), _lib.stream())
+            out = torch.cat([cmc.view(torch.uint8), summ]).cpu().numpy()          # one D2H copy, synchronises
+            cmc_host = out[: 4 * k_eff].view(np.float32).copy()
+            summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff:].tobytes())
+        raise_for_status(summary, self.max_rank)
+        info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first}
+        if return_distmat:
+            info["distmat"] = full
+        return cmc_host, float(summary.mAP), info
+
+
+def evaluate(qf, gf, q_pids, g_pids, q_camids, g_camids, dist_metric="euclidean", normalize_feature=False, rerank=False,
+             ranks=(1, 5, 10, 20), max_rank=20, precision=None, verbose=True, dataset_name=""):
+    """Tail of ``Engine._evaluate`` (engine.py:391-441) on one GPU.  Feature tensors may live on the host
+    (copied once) or on the device.  Prints the reference's result lines (engine.py:420-425), which
+    tools/parse_test_res.py:70 parses, and returns (cmc, mAP)."""
+    _lib.require_cuda()
+    dev = qf.device if qf.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    qf = qf.to(dev, non_blocking=True)
+    gf = gf.to(dev, non_blocking=True)
+    if verbose and normalize_feature:
+        print("Normalzing features with L2 norm ...")
+    if verbose:
+        print("Computing distance matrix with metric={} ...".format(dist_metric))
+    if not rerank:
+        ev = RetrievalEvaluator(gf, g_pids, g_camids, dist_metric, normalize_feature, precision, max_rank)
+        cmc, mAP, _ = ev.evaluate(qf, q_pids, q_camids)
+    else:
+        from .metrics.distance import _device_distmat
+        from .metrics.rank import evaluate_device
+        if verbose:
+            print("Applying person re-ranking ...")
+        qg = _device_distmat(qf, gf, dist_metric, normalize_feature, precision)
+        qq = _device_distmat(qf, qf, dist_metric, normalize_feature, precision)
+        gg = _device_distmat(gf, gf, dist_metric, normalize_feature, precision)
+        distmat = re_ranking_device(qg, qq, gg)
+        cmc_t, summary, _ = evaluate_device(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
+        raise_for_status(summary, max_rank)
+        cmc, mAP = cmc_t.cpu().numpy(), float(summary.mAP)
+    if verbose:
+        print("Computing CMC and mAP for {}".format(dataset_name))
+        print("** Results **")
+        print("mAP: {:.2%}".format(mAP))
+        print("CMC curve")
+        for r in ranks:
+            if r - 1 < len(cmc):
+                print("Rank-{:<3}: {:.2%}".format(r, cmc[r - 1]))
+        print("\n")
+    return cmc, mAP

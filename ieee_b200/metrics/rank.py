@@ -1,0 +1,173 @@
+"""Drop-in for torchreid/metrics/rank.py (Market-1501 protocol), computed on the GPU without sorting.
+
+``evaluate_rank`` keeps the reference signature and return types (rank.py:246-287): NumPy (or torch)
+arrays in, ``(cmc float32[min(max_rank, G)], mAP float)`` out.  As in this fork the Python Market-1501
+protocol is what runs (rank.py:278-287, ``use_cython`` is ignored) -- here it runs in
+``libieee_b200.so`` (ieee_b200/csrc/rank.cu): ties are ranked by gallery index, AP is float64.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _as_device(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype, non_blocking=True)
+
+
+class GalleryLabels:
+    """Gallery ids on the device plus their pid-sorted grouping (built once, reused per query block)."""
+
+    def __init__(self, g_pids, g_camids, device):
+        self.pids = _as_device(g_pids, torch.int64, device)
+        self.camids = _as_device(g_camids, torch.int64, device)
+        self.G = self.pids.numel()
+        assert self.camids.numel() == self.G
+        lib = _lib.load()
+        self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
+        self._scratch = torch.zeros(64, dtype=torch.int32, device=device)
+
+    def list_cap(self, q_pids: torch.Tensor) -> int:
+        cap = C.c_int32(0)
+        with torch.cuda.device(q_pids.device):
+            _lib.call("ieee_rank_list_cap_sync", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
+                      self._scratch.data_ptr(), C.byref(cap), _lib.stream())
+        return max(int(cap.value), 1)
+
+
+class RankStages:
+    """The three stream-ordered stages of include/ieee_b200.h (gather / count / finalize) over torch buffers."""
+
+    def __init__(self, Q: int, cap: int, shards: int, device):
+        self.Q, self.cap, self.shards, self.device = Q, cap, shards, device
+        self.rel = torch.empty((Q, cap), dtype=torch.int64, device=device)     # bit pattern of uint64 keys
+        self.junk = torch.empty((Q, cap), dtype=torch.int64, device=device)
+        self.n_rel = torch.empty(Q, dtype=torch.int32, device=device)
+        self.n_junk = torch.empty(Q, dtype=torch.int32, device=device)
+        self.counts = torch.empty((Q, shards * cap + 1), dtype=torch.int32, device=device)
+        self.flags = torch.zeros(8, dtype=torch.int64, device=device)          # [0] overflow (int32), [1] ties (uint64)
+        self.cmc = None
+        self.summary = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=device)
+        self.ap = torch.empty(Q, dtype=torch.float64, device=device)
+        self.first = torch.empty(Q, dtype=torch.int32, device=device)
+        self.ws = torch.empty(_lib.load().ieee_rank_finalize_workspace_bytes(Q), dtype=torch.uint8, device=device)
+
+    def gather(self, distmat, q_pids, q_camids, gal: GalleryLabels, g_offset: int = 0):
+        self.flags.zero_()
+        _lib.call("ieee_rank_gather", distmat.data_ptr(), distmat.stride(0), self.Q, gal.G, q_pids.data_ptr(),
+                  q_camids.data_ptr(), gal.camids.data_ptr(), gal.group.data_ptr(), g_offset, self.cap,
+                  self.rel.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
+                  self.flags.data_ptr(), _lib.stream())
+
+    def count(self, distmat, G: int, g_offset: int = 0, rel_all=None, n_rel_all=None):
+        rel_all = self.rel if rel_all is None else rel_all
+        n_rel_all = self.n_rel if n_rel_all is None else n_rel_all
+        _lib.call("ieee_rank_count", distmat.data_ptr(), distmat.stride(0), self.Q, G, g_offset, self.shards, self.cap,
+                  rel_all.data_ptr(), n_rel_all.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
+                  self.counts.data_ptr(), self.flags.data_ptr() + 8, _lib.stream())
+
+    def finalize(self, G_total: int, max_rank: int, n_rel_all=None, counts=None, ties=None):
+        n_rel_all = self.n_rel if n_rel_all is None else n_rel_all
+        counts = self.counts if counts is None else counts
+        k_eff = min(max_rank, G_total)
+        self.cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
+        ties_ptr = self.flags.data_ptr() + 8 if ties is None else ties.data_ptr()
+        _lib.call("ieee_rank_finalize", counts.data_ptr(), n_rel_all.data_ptr(), self.Q, G_total, self.shards, self.cap,
+                  max_rank, ties_ptr, self.cmc.data_ptr(), self.summary.data_ptr(), self.ap.data_ptr(),
+                  self.first.data_ptr(), self.ws.data_ptr(), _lib.stream())
+
+    def read_summary(self) -> _lib.EvalSummary:
+        raw = self.summary.cpu().numpy().tobytes()      # synchronises
+        return _lib.EvalSummary.from_buffer_copy(raw)
+
+
+def raise_for_status(s: _lib.EvalSummary, max_rank: int):
+    if s.status == _lib.ERR_NO_VALID_QUERY:     # rank.py:165
+        raise AssertionError("Error: all query identities do not appear in gallery")
+    if s.status == _lib.ERR_SHORT_RANK_LIST:    # rank.py:150,167 would build a ragged array here
+        raise ValueError("{} valid queries keep fewer than max_rank={} gallery samples after removing "
+                         "same-pid/same-camid entries".format(s.num_short, max_rank))
+
+
+def evaluate_device(distmat: torch.Tensor, q_pids, g_pids, q_camids, g_camids, max_rank: int,
+                    gallery: GalleryLabels | None = None):
+    """Device-resident evaluate_rank: returns (cmc tensor, EvalSummary, RankStages)."""
+    dev = distmat.device
+    with torch.cuda.device(dev):
+        Q, G = distmat.shape
+        qp = _as_device(q_pids, torch.int64, dev)
+        qc = _as_device(q_camids, torch.int64, dev)
+        gal = gallery if gallery is not None else GalleryLabels(g_pids, g_camids, dev)
+        assert qp.numel() == Q and qc.numel() == Q and gal.G == G
+        st = RankStages(Q, gal.list_cap(qp), 1, dev)
+        st.gather(distmat, qp, qc, gal)
+        st.count(distmat, G)
+        st.finalize(G, max_rank)
+        return st.cmc, st.read_summary(), st
+
+
+def eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank):
+    """Evaluation with market1501 metric (reference: rank.py:103-171).
+    Key: for each query identity, its gallery images from the same camera view are discarded."""
+    _lib.require_cuda()
+    dev = distmat.device if isinstance(distmat, torch.Tensor) and distmat.is_cuda else torch.device(
+        "cuda", torch.cuda.current_device())
+    d = _as_device(distmat, torch.float32, dev)
+    assert d.dim() == 2
+    num_q, num_g = d.shape
+    if num_g < max_rank:
+        max_rank = num_g
+        print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    cmc, summary, _ = evaluate_device(d, q_pids, g_pids, q_camids, g_camids, max_rank)
+    raise_for_status(summary, max_rank)
+    return cmc.cpu().numpy(), float(summary.mAP)
+
+
+def evaluate_py(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, use_metric_cuhk03):
+    if use_metric_cuhk03:
+        # rank.py:236-239 passes 6 arguments to the 8-argument eval_cuhk03, so the reference raises
+        # TypeError on this branch; the single-gallery-shot protocol is out of scope.
+        raise TypeError("eval_cuhk03() missing 2 required positional arguments: 'g_camids' and 'max_rank' "
+                        "(the reference's cuhk03 branch is unreachable; only the Market-1501 protocol is provided)")
+    return eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
+
+
+def evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=20, use_metric_cuhk03=False, use_cython=True):
+    """Evaluates CMC rank (reference: rank.py:246-287).
+
+    Args:
+        distmat (numpy.ndarray | torch.Tensor): distance matrix of shape (num_query, num_gallery); a CUDA
+            tensor is used in place (no copy).
+        q_pids, g_pids, q_camids, g_camids: 1-D integer arrays (identities / camera views).
+        max_rank (int, optional): maximum CMC rank to be computed. Default is 20 (rank.py:252).
+        use_metric_cuhk03 (bool, optional): raises TypeError, as the reference does (rank.py:236-239).
+        use_cython (bool, optional): accepted and ignored, as in the reference (rank.py:278-287).
+    """
+    return evaluate_py(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, use_metric_cuhk03)
+
+
+def topk_ranked_list(distmat, q_pids=None, g_pids=None, q_camids=None, g_camids=None, k=20, g_offset=0):
+    """First k entries of every query's junk-filtered ranked list (rank.py:117 + :136-140; what
+    torchreid/utils/reidtools.py:49,111 walks).  Pass no labels for an unmasked top-k.
+    Returns (idx int32 [Q,k] global gallery indices, -1 padded; dist float32 [Q,k]) on the device."""
+    _lib.require_cuda()
+    dev = distmat.device if isinstance(distmat, torch.Tensor) and distmat.is_cuda else torch.device(
+        "cuda", torch.cuda.current_device())
+    d = _as_device(distmat, torch.float32, dev)
+    Q, G = d.shape
+    idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    val = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    masked = q_pids is not None
+    lab = [(_as_device(x, torch.int64, dev) if masked else None) for x in (q_pids, q_camids, g_pids, g_camids)]
+    with torch.cuda.device(dev):
+        _lib.call("ieee_topk", d.data_ptr(), d.stride(0), Q, G, g_offset, _lib.ptr(lab[0]), _lib.ptr(lab[1]),
+                  _lib.ptr(lab[2]), _lib.ptr(lab[3]), k, idx.data_ptr(), val.data_ptr(), _lib.stream())
+    return idx, val

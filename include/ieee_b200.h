@@ -1,0 +1,206 @@
+/*
+ * ieee_b200.h -- C ABI of libieee_b200.so: the B200 (sm_100a) implementation of the
+ * test-time retrieval hot path of ziwang1121/IEEE (a torchreid fork).
+ *
+ * The reference has no FFI for this path: it is three Python module-level functions plus one
+ * CPython extension (file:line relative to the reference tree):
+ *
+ *   torchreid/metrics/distance.py:6          compute_distance_matrix(input1, input2, metric)
+ *   torchreid/metrics/rank.py:246            evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, ...)
+ *   torchreid/metrics/rank_cylib/rank_cy.pyx:26   evaluate_cy(...)          (the one native seam)
+ *   torchreid/utils/rerank.py:31             re_ranking(q_g_dist, q_q_dist, g_g_dist, k1, k2, lambda_value)
+ *   torchreid/engine/engine.py:391-417       Engine._evaluate: normalise -> distmat -> [rerank] -> evaluate_rank
+ *
+ * The entry points below are what a binding for those functions calls (ctypes stub in
+ * INTEGRATION.md; ieee_b200/_lib.py is that stub).  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - nothing is allocated on the caller's behalf: outputs and workspaces are passed in, workspace
+ *     sizes come from the matching *_workspace_bytes() function; workspaces need 256-byte alignment;
+ *   - all work is enqueued on `stream` (a cudaStream_t) and is asynchronous unless the function
+ *     name ends in _sync;
+ *   - return value: IEEE_OK or an ieee_status; ieee_last_error() gives the text (thread local);
+ *   - no CPU fallback anywhere: without a CUDA device every compute call returns IEEE_ERR_CUDA.
+ *
+ * Matrices are row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef IEEE_B200_H_
+#define IEEE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IEEE_B200_ABI_VERSION 1
+
+typedef void* ieee_stream_t; /* cudaStream_t */
+
+typedef enum {
+  IEEE_OK = 0,
+  IEEE_ERR_INVALID = 1,        /* bad argument (shape, alignment, enum)                        */
+  IEEE_ERR_CUDA = 2,           /* CUDA runtime / driver error, or no device                    */
+  IEEE_ERR_WORKSPACE = 3,      /* workspace too small or misaligned                            */
+  IEEE_ERR_NO_VALID_QUERY = 4, /* rank.py:165 "all query identities do not appear in gallery" */
+  IEEE_ERR_SHORT_RANK_LIST = 5,/* a valid query keeps fewer than max_rank gallery items
+                                  (ragged ValueError in rank.py:167, stale buffer in rank_cy.pyx) */
+  IEEE_ERR_CAPACITY = 6        /* a per-query list exceeded the capacity given by the caller   */
+} ieee_status;
+
+typedef enum { IEEE_METRIC_EUCLIDEAN = 0, IEEE_METRIC_COSINE = 1 } ieee_metric;      /* distance.py:36-44 */
+typedef enum { IEEE_DTYPE_F32 = 0, IEEE_DTYPE_BF16 = 1 } ieee_dtype;
+
+/* Arithmetic of the distance contraction (always fp32 accumulation in TMEM / registers):
+ *   BF16X3    fp32 features split into bf16 hi+lo, three tcgen05 MMAs per k-step (hi*hi, hi*lo, lo*hi):
+ *             fp32-equivalent products; the mode that meets the 1e-4 parity bound for fp32 inputs.
+ *   BF16      one tcgen05 MMA per k-step on bf16-rounded features (exact for bf16 inputs).
+ *   FP32_SIMT plain fp32 FMA kernel (no tensor cores); cross-check for the tensor path.           */
+typedef enum { IEEE_PREC_BF16X3 = 0, IEEE_PREC_BF16 = 1, IEEE_PREC_FP32_SIMT = 2 } ieee_precision;
+
+const char* ieee_last_error(void);
+int ieee_abi_version(void);
+/* Number of SMs / compute capability (major*10+minor) of the current device; IEEE_ERR_CUDA without one. */
+int ieee_device_info(int* sm_count, int* compute_capability);
+/* Tensor-core kernel pairing: 2 (default) = tcgen05 cta_group::2, one 256 x 256 tile per SM pair;
+ * 1 = cta_group::1, one 128 x 256 tile per SM.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
+int ieee_set_cta_group(int cta_group);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
+int64_t ieee_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Distance matrix.   Replaces distance.py:49-64 (euclidean_squared_distance: ||a||^2 + ||b||^2 - 2ab^T,
+ * squared, unclamped) and distance.py:67-80 (cosine_distance: 1 - normalize(a) normalize(b)^T, eps 1e-12).
+ * `normalize` != 0 applies engine.py:391-394 (F.normalize of both sets) first.
+ *
+ * Packed operand = what the tensor-core kernel consumes: bf16 hi plane (+ lo plane for BF16X3), each
+ * [rows, Dp] with Dp = D rounded up to 64, zero padded, plus one fp32 per row (squared norm for
+ * euclidean, unused for cosine).  Pack a gallery once, reuse it for every query block.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision);
+int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,
+                       int precision, void* packed, ieee_stream_t stream);
+int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                        int precision, float* out, int64_t ldo, ieee_stream_t stream);
+size_t ieee_distmat_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision);
+/* One call: pack both sides into the workspace, then the contraction.  out[Q, G] float32, leading dim ldo. */
+int ieee_distmat(const void* q, const void* g, int dtype, int64_t ldq, int64_t ldg, int64_t Q, int64_t G, int64_t D,
+                 int metric, int normalize, int precision, float* out, int64_t ldo, void* workspace,
+                 size_t workspace_bytes, ieee_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ranking + CMC / mAP, Market-1501 protocol.   Replaces rank.py:103-171 (eval_market1501) and
+ * rank_cy.pyx:156-243 (eval_market1501_cy).  Sort-free: the metrics depend only on the positions of the
+ * relevant gallery items among the kept ones, pos(r) = #{kept g : (d[q,g], g) <lex (d[q,r], r)} -- ties are
+ * broken by gallery index (the order the reference leaves to NumPy's unstable argsort), NaN ranks last.
+ *
+ * Three stream-ordered stages so that a gallery sharded over several GPUs can exchange between them:
+ *   group   : sort the (local) gallery by pid once                        -> ieee_gallery_group
+ *   gather  : per query, its relevant / junk gallery items and distances  -> ieee_rank_gather
+ *             [all-gather of the relevant lists across shards]
+ *   count   : one streaming pass over the (local) distance rows           -> ieee_rank_count
+ *             [all-reduce SUM of the integer counts across shards]
+ *   finalize: AP in fp64, CMC hit counts, means                           -> ieee_rank_finalize
+ * ieee_eval_market1501 runs all of them for the single-GPU case.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Result block written by ieee_rank_finalize / ieee_eval_market1501 (device memory, 64 bytes + cmc). */
+typedef struct {
+  double mAP;              /* mean of per-query AP over valid queries (float64, rank.py:169)            */
+  double sum_ap;           /* sum of AP (for merging query blocks: mAP = sum_ap / num_valid)            */
+  int64_t num_valid;       /* queries with at least one relevant kept gallery item (rank.py:142-144)    */
+  int64_t num_ties;        /* (relevant item, other kept item) pairs with bit-equal distance            */
+  int64_t num_short;       /* valid queries that keep fewer than max_rank gallery items                 */
+  int32_t max_rank;        /* effective K' = min(max_rank, G_total) (rank.py:110-115)                   */
+  int32_t status;          /* IEEE_OK / IEEE_ERR_NO_VALID_QUERY / IEEE_ERR_SHORT_RANK_LIST              */
+  int64_t reserved[2];
+} ieee_eval_summary;
+
+/* Sort the (local) gallery's ids once: the group blob holds (pid, local index) pairs in ascending pid order
+ * (padded to a power of two), so a query finds all gallery items of its identity by binary search instead of
+ * scanning G labels.  g_pids: int64[G], G < 2^31. */
+size_t ieee_gallery_group_bytes(int64_t G);
+int ieee_gallery_group(const int64_t* g_pids, int64_t G, void* group /* ieee_gallery_group_bytes(G) */,
+                       ieee_stream_t stream);
+/* Largest number of (local) gallery items sharing an identity with any of the Q queries = the list capacity
+ * `cap` the gather/count stages need.  scratch_dev: 4 bytes of device memory.  Synchronises the stream. */
+int ieee_rank_list_cap_sync(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* scratch_dev,
+                            int32_t* cap_host, ieee_stream_t stream);
+
+/* gather: for each of Q queries, rel[q, 0..n_rel[q]) = packed (orderable distance key << 32 | global gallery
+ * index) of the relevant local items (same pid, other camera), junk[q, ...] likewise for the junk items
+ * (same pid, same camera, rank.py:136).  `cap` = list capacity per query (>= max_group).  Unsorted.
+ * g_offset = global index of local gallery row 0 (0 on one GPU). */
+int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
+                     const int64_t* q_camids, const int64_t* g_camids, const void* group, int64_t g_offset,
+                     int32_t cap, uint64_t* rel, int32_t* n_rel, uint64_t* junk, int32_t* n_junk,
+                     int32_t* overflow_flag, ieee_stream_t stream);
+
+/* count: thresholds of query q = union over the `shards` relevant lists rel_all[s][q][cap] (the all-gathered
+ * buffers; shards = 1 and rel_all = rel on one GPU).  Streams the local distance row once and writes
+ * counts[q, k] = #{local kept g : (d, g) <lex T_k} for the k-th smallest threshold, k < n_rel_total[q]
+ * (= sum over shards), plus counts[q, shards*cap] = number of local junk items.  counts is
+ * int32[Q, shards*cap + 1]; it is summed over shards by the caller (all-reduce) before finalize.
+ * ties (int64[1], may be NULL) accumulates bit-equal (threshold, other kept item) pairs. */
+size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap);
+int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards,
+                    int32_t cap, const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk,
+                    const int32_t* n_junk, int32_t* counts, unsigned long long* ties, ieee_stream_t stream);
+
+/* finalize = ieee_rank_query_metrics (per query) followed by ieee_rank_reduce (over queries); the two halves
+ * are exported separately so that query blocks can share one final reduction.
+ *
+ * query_metrics: pos_k = counts[q,k] (already summed over shards); ap[q] = (1/R) sum_k (k+1)/(pos_k+1) in
+ * float64 (rank.py:155-160), first[q] = pos_0 (-1: invalid query, rank.py:142-144), short_list[q] = 1 when
+ * the query keeps fewer than max_rank gallery items.  G_total = gallery size over all shards.
+ * reduce: cmc[0..K') float32 = float32(hits_j) / float32(num_valid) exactly as rank.py:167-168 and
+ * mAP = mean(ap) (float64, fixed reduction tree: bitwise reproducible), K' = min(max_rank, G_total). */
+int ieee_rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+                            int32_t cap, int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
+                            ieee_stream_t stream);
+int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
+                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, ieee_stream_t stream);
+/* per_query_ap (double[Q]) / per_query_first (int32[Q]) may be NULL.  workspace: ieee_rank_finalize_workspace_bytes(Q). */
+size_t ieee_rank_finalize_workspace_bytes(int64_t Q);
+int ieee_rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+                       int32_t cap, int32_t max_rank, const unsigned long long* ties, float* cmc,
+                       ieee_eval_summary* summary, double* per_query_ap, int32_t* per_query_first, void* workspace,
+                       ieee_stream_t stream);
+
+/* Single-GPU evaluate_rank on a device distmat: group + gather + count + finalize.  Synchronises the stream
+ * once (ieee_rank_list_cap_sync) to size the per-query lists.  `cap` = list capacity the workspace was sized
+ * for (0: sized with the default of ieee_eval_workspace_bytes); IEEE_ERR_CAPACITY if a query needs more.
+ * cmc: float[max_rank] device, summary: device. */
+size_t ieee_eval_workspace_bytes(int64_t Q, int64_t G, int32_t cap /* 0 = min(G, 4096) */);
+int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
+                         const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
+                         int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
+                         ieee_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Junk-masked top-k ranked list: the first k entries of rank.py:117 + :136-140 per query (what
+ * torchreid/utils/reidtools.py:49,111 walks), ascending (distance, index); rows with fewer than k kept
+ * items are padded with index -1 / +inf.  Pass q_pids = NULL for an unmasked top-k (re-ranking, rerank.py:48).
+ * idx: int32[Q, k] GLOBAL gallery indices (local + g_offset), val: float[Q, k].  k <= 1024.
+ * ---------------------------------------------------------------------------------------------- */
+int ieee_topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
+              const int64_t* q_camids, const int64_t* g_pids, const int64_t* g_camids, int32_t k, int32_t* idx,
+              float* val, ieee_stream_t stream);
+/* Merge `shards` per-shard top-k lists (idx_all[s][Q][k], val_all[s][Q][k]) into the global top-k. */
+int ieee_topk_merge(const int32_t* idx_all, const float* val_all, int32_t shards, int64_t Q, int32_t k,
+                    int32_t* idx, float* val, ieee_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * k-reciprocal re-ranking.   Replaces rerank.py:31-113.  Inputs are the three device distance matrices
+ * (float32): q_g [Q,G], q_q [Q,Q], g_g [G,G]; out: float32 [Q, G] (leading dim ldo).
+ * ---------------------------------------------------------------------------------------------- */
+size_t ieee_rerank_workspace_bytes(int64_t Q, int64_t G, int32_t k1, int32_t k2);
+int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, const float* g_g, int64_t ld_gg,
+                int64_t Q, int64_t G, int32_t k1, int32_t k2, float lambda_value, float* out, int64_t ldo,
+                void* workspace, size_t workspace_bytes, ieee_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IEEE_B200_H_ */

@@ -1,0 +1,65 @@
+"""CPU checks of the C-ABI boundary: the library loads without a GPU and exports what the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from ieee_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "ieee_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ieee_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_path():
+    names = header_functions()
+    for required in ("ieee_distmat", "ieee_eval_market1501", "ieee_topk", "ieee_rerank", "ieee_rank_gather",
+                     "ieee_rank_count", "ieee_rank_finalize", "ieee_last_error"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ieee_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in ieee_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == header_functions()
+
+
+def test_abi_version_and_struct_layout():
+    lib = _lib.load()
+    assert lib.ieee_abi_version() == 1
+    assert ctypes.sizeof(_lib.EvalSummary) == 64
+
+
+def test_size_queries_need_no_gpu():
+    lib = _lib.load()
+    # hi + lo planes of [rows, roundup(D,64)] bf16 plus one fp32 per row, 256-byte aligned sections
+    assert lib.ieee_packed_bytes(128, 2304, _lib.PRECISIONS["bf16x3"]) == 2 * 128 * 2304 * 2 + 512
+    assert lib.ieee_packed_bytes(128, 100, _lib.PRECISIONS["bf16"]) == 128 * 128 * 2 + 512
+    assert lib.ieee_gallery_group_bytes(15913) == 16384 * 12
+    assert lib.ieee_rank_finalize_workspace_bytes(1000) > 0
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_cpu_fallback():
+    import torch
+    from ieee_b200.metrics import compute_distance_matrix, evaluate_rank
+    lib = _lib.load()
+    sm, cc = ctypes.c_int(), ctypes.c_int()
+    assert lib.ieee_device_info(ctypes.byref(sm), ctypes.byref(cc)) == _lib.ERR_CUDA
+    assert b"no CPU fallback" in lib.ieee_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        compute_distance_matrix(torch.rand(4, 8), torch.rand(5, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        evaluate_rank(torch.rand(4, 5).numpy(), [1] * 4, [1] * 5, [0] * 4, [1] * 5)
+    # argument errors keep the reference's exception types even without a GPU (distance.py:26-44)
+    with pytest.raises(ValueError):
+        compute_distance_matrix(torch.rand(4, 8), torch.rand(5, 8), "manhattan")
+    with pytest.raises(AssertionError):
+        compute_distance_matrix(torch.rand(4, 8), torch.rand(5, 9))

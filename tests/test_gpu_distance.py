@@ -1,0 +1,129 @@
+"""GPU parity: distance matrix through the drop-in API / C ABI vs the CPU oracle (same seeded inputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from ieee_b200 import _lib
+from ieee_b200.metrics import compute_distance_matrix
+from ieee_b200.metrics.distance import _device_distmat
+from ieee_b200.testing import make_retrieval_set, rgbnt201_shaped
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # north_star: distances within 1e-4 relative in fp32
+CANCEL_ULPS = 4e-7   # a few fp32 ulps of |q|^2 + |g|^2: the cancellation floor the reference itself sits on (F7)
+
+
+def assert_distance_parity(got, a, b, metric, rtol=RTOL):
+    """|got - fp64 truth| <= rtol*|truth| + cancellation floor; and no worse than ~the reference's own error."""
+    truth = R.distance_fp64(a, b, metric).numpy()
+    ref = R.compute_distance_matrix(a, b, metric).numpy()
+    scale = ((a.double() ** 2).sum(1, keepdim=True) + (b.double() ** 2).sum(1, keepdim=True).t()).numpy() \
+        if metric == "euclidean" else np.full_like(truth, 2.0)
+    tol = rtol * np.abs(truth) + CANCEL_ULPS * scale
+    err = np.abs(got.astype(np.float64) - truth)
+    assert (err <= tol).all(), f"max err/tol = {(err / tol).max():.3g}"
+    # same yardstick for the reference's fp32 result, reported for the record
+    ref_err = np.abs(ref.astype(np.float64) - truth)
+    return float((err / np.maximum(np.abs(truth), 1e-30)).max()), float(err.max()), float(ref_err.max())
+
+
+def features(q, g, d, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.relu(torch.randn(q, d, generator=gen) + 0.3), torch.relu(torch.randn(g, d, generator=gen) + 0.3)
+
+
+@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_group2"])
+def cta_group(request):
+    prev = _lib.load().ieee_set_cta_group(request.param)
+    yield request.param
+    _lib.load().ieee_set_cta_group(prev)
+
+
+SHAPES = [(10, 100, 2048), (1, 1, 64), (130, 300, 96), (257, 513, 2304), (128, 256, 64), (300, 1000, 200), (5, 7, 3)]
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_bf16x3_matches_oracle(cta_group, shape, metric):
+    a, b = features(*shape, seed=sum(shape))
+    out = compute_distance_matrix(a.cuda(), b.cuda(), metric)
+    assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == shape[:2]
+    assert_distance_parity(out.cpu().numpy(), a, b, metric)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_golden_distance(golden_dir, metric):
+    g = np.load(os.path.join(golden_dir, "distance_small.npz"))
+    a, b = torch.from_numpy(g["a"]), torch.from_numpy(g["b"])
+    out = compute_distance_matrix(a, b, metric)        # CPU tensors in -> CPU tensor out, like the reference
+    assert not out.is_cuda and out.dtype == torch.float32
+    np.testing.assert_allclose(out.numpy(), g[metric], rtol=1e-4, atol=1e-4 if metric == "euclidean" else 1e-6)
+    if metric == "cosine":
+        assert (out.numpy()[:, 3] == 1.0).all()        # all-zero row -> exactly 1 (distance.py:77-79)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_fp32_simt_matches_oracle(metric):
+    a, b = features(70, 130, 300, seed=5)
+    out = compute_distance_matrix(a.cuda(), b.cuda(), metric, precision="fp32_simt")
+    assert_distance_parity(out.cpu().numpy(), a, b, metric)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_bf16_single_pass_is_exact_for_bf16_inputs(cta_group, metric):
+    a, b = features(200, 700, 512, seed=9)
+    a16, b16 = a.bfloat16(), b.bfloat16()
+    out = compute_distance_matrix(a16.cuda(), b16.cuda(), metric)
+    assert out.dtype == torch.bfloat16                     # output dtype follows the inputs (distance.py)
+    got = _device_distmat(a16.cuda(), b16.cuda(), metric).cpu().numpy()
+    if metric == "euclidean":                              # products of bf16 values are exact in fp32
+        assert_distance_parity(got, a16.float(), b16.float(), metric)
+    else:                                                  # normalised rows are re-rounded to bf16: bf16-level accuracy
+        truth = R.distance_fp64(a16.float(), b16.float(), metric).numpy()
+        assert np.abs(got - truth).max() < 1e-2
+
+
+def test_tensor_path_agrees_with_simt_path(cta_group):
+    s = make_retrieval_set(300, 700, 30, 4, dim=2304, seed=2)
+    x3 = compute_distance_matrix(s.qf.cuda(), s.gf.cuda(), "euclidean").cpu().numpy()
+    simt = compute_distance_matrix(s.qf.cuda(), s.gf.cuda(), "euclidean", precision="fp32_simt").cpu().numpy()
+    assert np.abs(x3 - simt).max() <= 1e-4 * np.abs(simt).max()
+
+
+def test_normalize_feature_then_euclidean():
+    """engine.py:391-394 then distance.py:59-64."""
+    a, b = features(64, 200, 2304, seed=3)
+    an, bn = torch.nn.functional.normalize(a, p=2, dim=1), torch.nn.functional.normalize(b, p=2, dim=1)
+    got = _device_distmat(a.cuda(), b.cuda(), "euclidean", normalize=True).cpu().numpy()
+    assert_distance_parity(got, an, bn, "euclidean")
+
+
+def test_rgbnt201_shape_self_distances():
+    s = rgbnt201_shaped()
+    out = compute_distance_matrix(s.qf.cuda(), s.gf.cuda()).cpu().numpy()
+    rel, abs_err, ref_abs = assert_distance_parity(out, s.qf, s.gf, "euclidean")
+    diag = np.abs(np.diag(out))
+    assert diag.max() < 1e-6 * (s.qf ** 2).sum(1).max().item() * 4    # squared, unclamped, ~0 (F7)
+
+
+def test_argument_errors():
+    a, b = features(4, 5, 8)
+    with pytest.raises(ValueError):
+        compute_distance_matrix(a.cuda(), b.cuda(), "manhattan")
+    with pytest.raises(AssertionError):
+        compute_distance_matrix(a.cuda(), b.cuda()[:, :4])
+    with pytest.raises(AssertionError):
+        compute_distance_matrix(a.cuda()[0], b.cuda())
+    assert compute_distance_matrix(a.cuda()[:0], b.cuda()).shape == (0, 5)
+
+
+def test_noncontiguous_rows_and_views():
+    a, b = features(40, 90, 128, seed=8)
+    big = torch.zeros(40, 256).cuda()
+    big[:, :128] = a.cuda()
+    out = compute_distance_matrix(big[:, :128], b.cuda())        # row stride 256, unit column stride
+    assert_distance_parity(out.cpu().numpy(), a, b, "euclidean")

@@ -1,0 +1,175 @@
+"""GPU parity: evaluate_rank / top-k through the drop-in API and the C ABI vs the CPU oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref, restatement as R
+from ieee_b200 import _lib
+from ieee_b200.metrics import evaluate_rank
+from ieee_b200.metrics.rank import evaluate_device, topk_ranked_list
+from ieee_b200.testing import make_retrieval_set, market1501_shaped, rgbnt201_shaped
+
+pytestmark = pytest.mark.gpu
+
+
+def check_against_oracle(d, qp, gp, qc, gc, max_rank=20):
+    cmc_o, map_o = R.evaluate_rank(d, qp, gp, qc, gc, max_rank=max_rank)          # stable ties (gallery index)
+    cmc, mAP = evaluate_rank(d, qp, gp, qc, gc, max_rank=max_rank)
+    assert isinstance(cmc, np.ndarray) and cmc.dtype == np.float32 and isinstance(mAP, float)
+    assert np.array_equal(cmc, cmc_o), "CMC must be bit-exact"
+    assert abs(mAP - map_o) < 1e-9, (mAP, map_o)                                   # bar: 1e-6
+    return cmc, mAP
+
+
+@pytest.mark.parametrize("name", ["rank_cython_shape.npz", "rank_clustered.npz", "rank_ties_stable.npz"])
+def test_golden_rank(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    cmc, mAP = evaluate_rank(g["distmat"], g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"],
+                             max_rank=int(g["max_rank"]))
+    assert np.array_equal(cmc, g["cmc"]) and abs(mAP - float(g["mAP"])) < 1e-9
+
+
+def test_tie_count_reported(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rank_ties_stable.npz"))
+    d = torch.from_numpy(g["distmat"]).cuda()
+    _, summary, st = evaluate_device(d, g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"], 20)
+    # oracle tie count: (relevant r, kept non-relevant g) pairs with equal distance
+    want = 0
+    for q in range(d.shape[0]):
+        same = g["g_pids"] == g["q_pids"][q]
+        junk = same & (g["g_camids"] == g["q_camids"][q])
+        rel = same & ~junk
+        other = ~same
+        want += int((g["distmat"][q][rel][:, None] == g["distmat"][q][other][None, :]).sum())
+    assert summary.num_ties == want and want > 0
+    g2 = np.load(os.path.join(golden_dir, "rank_clustered.npz"))
+    _, s2, _ = evaluate_device(torch.from_numpy(g2["distmat"]).cuda(), g2["q_pids"], g2["g_pids"], g2["q_camids"],
+                               g2["g_camids"], 20)
+    assert s2.num_ties == 0
+
+
+def test_rgbnt201_shaped_with_natural_ties():
+    s = rgbnt201_shaped()
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()          # identical distmat bits for both sides
+    check_against_oracle(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    if ref.available() and R.count_row_ties(d) == 0:
+        cmc_r, map_r = ref.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+        cmc, mAP = evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+        assert np.array_equal(cmc, cmc_r) and abs(mAP - map_r) < 1e-9
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_clustered_sets_per_query_positions(metric):
+    s = make_retrieval_set(200, 3000, 40, 4, dim=256, sigma=2.5, seed=12, distractor_frac=0.15)
+    s.q_pids[:5] = 10 ** 12 + 7                                # int64 ids beyond int32, absent from the gallery
+    d = R.compute_distance_matrix(s.qf, s.gf, metric).numpy()
+    check_against_oracle(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, max_rank=50)
+    # per-query intermediates: first-hit rank and AP
+    _, _, info = R.eval_market1501(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, 50, return_info=True)
+    _, summary, st = evaluate_device(torch.from_numpy(d).cuda(), s.q_pids, s.g_pids, s.q_camids, s.g_camids, 50)
+    first = st.first.cpu().numpy()
+    assert np.array_equal(first, info["first_hit"])
+    ap = st.ap.cpu().numpy()[first >= 0]
+    np.testing.assert_allclose(ap, info["ap"], rtol=0, atol=1e-12)
+    assert summary.num_valid == info["num_valid"] == 195
+
+
+def test_heavy_ties_and_special_values():
+    rng = np.random.RandomState(3)
+    d = rng.randint(0, 12, size=(64, 500)).astype(np.float32)      # ~40 equal values per level
+    d[3, :50] = np.inf
+    d[4, 10:30] = -np.inf
+    d[5, ::7] = np.nan                                             # NaN ranks last (NumPy order)
+    d[6, :] = 1.0                                                  # every distance equal: pure index order
+    d[7, ::2] = -0.0
+    d[7, 1::2] = 0.0                                               # -0.0 == +0.0
+    qp, gp = rng.randint(0, 10, 64), rng.randint(0, 10, 500)
+    qc, gc = rng.randint(0, 3, 64), rng.randint(0, 3, 500)
+    check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
+
+
+def test_unaligned_rows_and_device_input():
+    s = make_retrieval_set(33, 1001, 12, 3, dim=64, sigma=2.0, seed=6)     # G odd: rows start at any 4-byte offset
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    padded = torch.zeros(33, 1003).cuda()
+    padded[:, 1:1002] = torch.from_numpy(d).cuda()
+    cmc, mAP = evaluate_rank(padded[:, 1:1002], torch.from_numpy(s.q_pids).cuda(), s.g_pids.astype(np.int32),
+                             s.q_camids.tolist(), torch.from_numpy(s.g_camids))
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - map_o) < 1e-9
+
+
+def test_max_rank_clamp_and_errors(capsys):
+    rng = np.random.RandomState(0)
+    d = rng.rand(6, 12).astype(np.float32)
+    qp, gp = np.arange(6) % 3, np.arange(12) % 3
+    qc, gc = np.zeros(6, int), np.ones(12, int)
+    cmc, mAP = evaluate_rank(d, qp, gp, qc, gc, max_rank=50)               # rank.py:110-115
+    assert cmc.shape == (12,) and "quite small" in capsys.readouterr().out
+    assert np.array_equal(cmc, R.evaluate_rank(d, qp, gp, qc, gc, max_rank=50)[0])
+    with pytest.raises(AssertionError, match="all query identities do not appear in gallery"):   # rank.py:165
+        evaluate_rank(d, qp + 100, gp, qc, gc)
+    with pytest.raises(TypeError):                                                              # rank.py:236-239
+        evaluate_rank(d, qp, gp, qc, gc, use_metric_cuhk03=True)
+    with pytest.raises(ValueError, match="fewer than max_rank"):     # all but 2 gallery items junk for query 0
+        gc2 = np.zeros(12, int); gp2 = np.zeros(12, int); gc2[:2] = 1
+        evaluate_rank(d, np.zeros(6, int), gp2, np.zeros(6, int), gc2, max_rank=5)
+
+
+def test_one_shot_c_entry_point():
+    """ieee_eval_market1501: the single call a C host would make."""
+    s = make_retrieval_set(50, 400, 10, 3, dim=64, sigma=2.0, seed=2)
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, max_rank=10)
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    dd = torch.from_numpy(d).to(dev)
+    lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.g_pids, s.q_camids, s.g_camids)]
+    cap = 128
+    nbytes = lib.ieee_eval_workspace_bytes(50, 400, cap)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    cmc = torch.empty(10, dtype=torch.float32, device=dev)
+    summ = torch.empty(64, dtype=torch.uint8, device=dev)
+    _lib.call("ieee_eval_market1501", dd.data_ptr(), 400, 50, 400, lab[0].data_ptr(), lab[1].data_ptr(),
+              lab[2].data_ptr(), lab[3].data_ptr(), 10, cap, cmc.data_ptr(), summ.data_ptr(), ws.data_ptr(), nbytes,
+              _lib.stream())
+    res = _lib.EvalSummary.from_buffer_copy(summ.cpu().numpy().tobytes())
+    assert np.array_equal(cmc.cpu().numpy(), cmc_o) and abs(res.mAP - map_o) < 1e-9 and res.status == 0
+    rc = lib.ieee_eval_market1501(dd.data_ptr(), 400, 50, 400, lab[0].data_ptr(), lab[1].data_ptr(), lab[2].data_ptr(),
+                                  lab[3].data_ptr(), 10, 2, cmc.data_ptr(), summ.data_ptr(), ws.data_ptr(), nbytes,
+                                  _lib.stream())
+    assert rc == _lib.ERR_CAPACITY
+
+
+@pytest.mark.parametrize("k", [1, 20, 21, 100])
+def test_topk_ranked_list(k):
+    s = make_retrieval_set(60, 2500, 20, 4, dim=64, sigma=2.0, seed=k)
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    d[:, ::5] = np.round(d[:, ::5])                                        # inject ties
+    idx_o, val_o = R.topk_kept(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, k)
+    idx, val = topk_ranked_list(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, k=k)
+    assert np.array_equal(idx.cpu().numpy(), idx_o) and np.array_equal(val.cpu().numpy(), val_o)
+    # unmasked variant == plain stable argsort prefix (rerank.py:48)
+    idx_u, _ = topk_ranked_list(d, k=k)
+    assert np.array_equal(idx_u.cpu().numpy(), np.argsort(d, axis=1, kind="stable")[:, :k])
+
+
+def test_topk_fewer_kept_than_k():
+    d = np.arange(12, dtype=np.float32).reshape(2, 6)
+    idx, val = topk_ranked_list(d, [1, 2], [1, 1, 1, 2, 2, 3], [0, 0], [0, 0, 1, 0, 1, 1], k=6)
+    assert idx.cpu().tolist() == [[2, 3, 4, 5, -1, -1], [0, 1, 2, 4, 5, -1]]
+    assert np.isinf(val.cpu().numpy()[0, 4:]).all()
+
+
+def test_market1501_shape_full_size():
+    """Config C2 at full size: 3368 x 15913, euclidean; oracle fed the SAME distmat bits."""
+    s = market1501_shaped()
+    from ieee_b200.metrics import compute_distance_matrix
+    d_dev = compute_distance_matrix(s.qf.cuda(), s.gf.cuda())
+    d = d_dev.cpu().numpy()
+    cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    cmc, mAP = evaluate_rank(d_dev, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - map_o) < 1e-9 and 0.05 < mAP < 0.95
