@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libieee_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_VALID_QUERY, ERR_SHORT_RANK_LIST, ERR_CAPACITY = range(7)
 METRICS = {"euclidean": 0, "cosine": 1}
-PRECISIONS = {"bf16x3": 0, "bf16": 1, "fp32_simt": 2}
+PRECISIONS = {"f16x3": 0, "bf16": 1, "fp32_simt": 2}
 DTYPES = {torch.float32: 0, torch.bfloat16: 1}
 
 i64, i32, sz, vp, f32 = C.c_int64, C.c_int32, C.c_size_t, C.c_void_p, C.c_float
@@ -30,6 +30,7 @@ SIGNATURES = {
     "ieee_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ieee_set_cta_group": (C.c_int, [C.c_int]),
     "ieee_launch_count": (i64, []),
+    "ieee_set_debug_flags": (C.c_int, [C.c_int]),
     "ieee_packed_bytes": (sz, [i64, i64, C.c_int]),
     "ieee_pack_features": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ieee_distmat_packed": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp]),

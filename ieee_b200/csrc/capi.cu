@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_error; }
 
 static std::atomic<long long> g_launches{0};
+int g_debug_flags = 0;
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
@@ -65,11 +66,11 @@ int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, con
            int64_t G, int32_t k1, int32_t k2, float lambda_value, float* out, int64_t ldo, void* workspace,
            size_t workspace_bytes, cudaStream_t stream);
 
-static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default pairing of the tensor-core kernel
+static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default (1) pairing of the tensor-core kernel
 static int cta_group_default() {
   if (g_cta_group < 0) {
     const char* e = getenv("IEEE_B200_CTA_GROUP");
-    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+    g_cta_group = (e && e[0] == '2') ? 2 : 1;
   }
   return g_cta_group;
 }
@@ -119,6 +120,12 @@ int ieee_device_info(int* sm, int* cc) {
 
 int64_t ieee_launch_count(void) { return g_launches.load(); }
 
+int ieee_set_debug_flags(int flags) {
+  const int prev = g_debug_flags;
+  g_debug_flags = flags;
+  return prev;
+}
+
 int ieee_set_cta_group(int cg) {
   const int prev = cta_group_default();
   if (cg == 1 || cg == 2) g_cta_group = cg;
@@ -149,7 +156,7 @@ int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, i
   IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
   if (Q == 0 || G == 0) return IEEE_OK;
   if (precision == IEEE_PREC_FP32_SIMT) return distmat_simt(q_packed, Q, g_packed, G, D, metric, out, ldo, (cudaStream_t)stream);
-  IEEE_REQUIRE(precision == IEEE_PREC_BF16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
+  IEEE_REQUIRE(precision == IEEE_PREC_F16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
   return distmat_umma(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, (cudaStream_t)stream, cta_group_default());
 }
 

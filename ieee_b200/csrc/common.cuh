@@ -37,7 +37,8 @@ const char* get_error();
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
-void count_launch(int n = 1);   // bookkeeping behind ieee_launch_count()
+void count_launch(int n = 1);
+extern int g_debug_flags;       // ieee_set_debug_flags()   // bookkeeping behind ieee_launch_count()
 
 // ---- total order on float distances -----------------------------------------------------------------
 // Ascending uint32 key == NumPy's ascending sort order: -0.0 == +0.0, every NaN equal and last.
@@ -67,10 +68,11 @@ __host__ __device__ __forceinline__ uint64_t pack_key(float d, uint32_t idx) {
 }
 
 // ---- packed operand layout (ieee_pack_features) ------------------------------------------------------
-// [hi plane: rows x Dp bf16][lo plane (BF16X3 only)][norms: rows fp32], each section 256-byte aligned.
+// [hi plane: rows x Dp 16-bit][lo plane (F16X3 only)][norms: rows fp32][row scale: rows fp32], 256-byte aligned
+// sections.  FP32_SIMT: [fp32 plane rows x Dp][norms][row scale].
 struct PackedLayout {
   int64_t rows, D, Dp;
-  size_t hi_off, lo_off, norm_off, total;
+  size_t hi_off, lo_off, norm_off, scale_off, total;
   bool has_lo;
 };
 inline PackedLayout packed_layout(int64_t rows, int64_t D, int precision) {
@@ -78,18 +80,14 @@ inline PackedLayout packed_layout(int64_t rows, int64_t D, int precision) {
   L.rows = rows;
   L.D = D;
   L.Dp = round_up(D, 64);
-  L.has_lo = (precision == IEEE_PREC_BF16X3);
-  size_t plane = align256(size_t(rows) * size_t(L.Dp) * 2);
+  L.has_lo = (precision == IEEE_PREC_F16X3);
+  const size_t esz = precision == IEEE_PREC_FP32_SIMT ? 4 : 2;
+  const size_t plane = align256(size_t(rows) * size_t(L.Dp) * esz);
   L.hi_off = 0;
-  L.lo_off = plane;
+  L.lo_off = L.has_lo ? plane : 0;
   L.norm_off = L.has_lo ? 2 * plane : plane;
-  L.total = L.norm_off + align256(size_t(rows) * 4);
-  if (precision == IEEE_PREC_FP32_SIMT) {  // fp32 plane (row pitch Dp) + norms
-    size_t p32 = align256(size_t(rows) * size_t(L.Dp) * 4);
-    L.lo_off = 0;
-    L.norm_off = p32;
-    L.total = p32 + align256(size_t(rows) * 4);
-  }
+  L.scale_off = L.norm_off + align256(size_t(rows) * 4);
+  L.total = L.scale_off + align256(size_t(rows) * 4);
   return L;
 }
 
@@ -176,6 +174,22 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar
       "[%2];" ::"r"(smem_u32(smem)),
       "l"(desc), "r"(mbar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// smem tile -> global through a tensor map (clips rows / columns outside the tensor); bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -271,10 +285,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
-// Instruction descriptor, kind::f16: D fp32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17,
+// Instruction descriptor, kind::f16: D fp32 (bit 4), A and B format at bits 7 / 10, both K-major, N >> 3 at bit 17,
 // M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_16bit(uint32_t M, uint32_t N, uint32_t fmt /* 0 f16, 1 bf16 */) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 #endif  // __CUDACC__
 

@@ -6,15 +6,16 @@
 //
 // Kernel shape (persistent, warp specialised, one CTA per SM):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) into a kStages smem ring
-//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (kind::f16, bf16 in, fp32 accumulate in TMEM)
+//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (kind::f16, fp16/bf16 in, fp32 accumulate in TMEM)
 //   warp 2   : TMEM allocator -- 512 columns = two 128 x 256 fp32 accumulator stages
-//   warps 4-7: epilogue       -- tcgen05.ld -> registers -> smem transpose -> coalesced global stores of
-//                                d = fma(alpha, acc, rq[row] + rg[col])
+//   warps 4-7: epilogue       -- tcgen05.ld -> d = fma(coef[row] * sg[col], acc, rq[row] + rg[col]) in registers ->
+//                                swizzled smem tile -> TMA store (clips the ragged edges); a transposing
+//                                st.global path serves outputs whose row pitch is not a multiple of 16 bytes
 // kCtaGroup == 2 pairs two SMs on one 256 x 256 tile (tcgen05.mma.cta_group::2): each CTA loads its own 128
-// rows of A and HALF of the B tile, so per-SM shared-memory and L2 traffic per flop halves.
+// rows of A and HALF of the B tile.
 //
-// BF16X3 (fp32-equivalent) mode runs three k-passes per 64-wide k block into the same accumulator:
-// (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi).
+// F16X3 (fp32-grade) mode runs three k-passes per 64-wide k block into the same accumulator:
+// (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi); rows were scaled by powers of two when packed, undone by sq/sg here.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,11 +24,11 @@ namespace ieee {
 
 constexpr int BLOCK_M = 128;  // rows of A per CTA == TMEM lanes
 constexpr int BLOCK_N = 256;  // columns per tile == UMMA N
-constexpr int BLOCK_K = 64;   // bf16 elements per k block == one 128-byte swizzle span
+constexpr int BLOCK_K = 64;   // 16-bit elements per k block == one 128-byte swizzle span
 constexpr int UMMA_K = 16;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 128 + 32 * kEpilogueWarps;
-constexpr int kStagePitch = 33;  // floats; padded 32 x 32 transpose tile per epilogue warp
+constexpr int kStagePitch = 33;  // floats; padded 32 x 32 transpose tile (fallback epilogue)
 
 template <int CG>
 struct GemmCfg {
@@ -36,36 +37,47 @@ struct GemmCfg {
   static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
   static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;        // 32 KB / 16 KB
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kEpiBytes = kEpilogueWarps * 32 * kStagePitch * 4;
+  // per epilogue warp: 32 x 32 fp32 output tile (4 KB, 1024-aligned for SWIZZLE_128B; the fallback's padded
+  // 32 x 33 tile needs 4224 B) + the tile's 256 column terms rg / sg
+  static constexpr uint32_t kEpiTileBytes = 5 * 1024;
+  static constexpr uint32_t kEpiColBytes = 2 * BLOCK_N * 4;
+  static constexpr uint32_t kEpiWarpBytes = 7 * 1024;              // keeps every warp's tile 1024-byte aligned
+  static constexpr uint32_t kEpiBytes = kEpilogueWarps * kEpiWarpBytes;
   static constexpr uint32_t kBarBytes = 256;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /* alignment slack */;
+  static_assert(kEpiTileBytes + kEpiColBytes <= kEpiWarpBytes, "epilogue smem carve");
 };
 
 struct GemmParams {
-  const float* rq;   // per query row term (euclidean: squared norm; cosine: nullptr -> 1)
-  const float* rg;   // per gallery row term (euclidean: squared norm; cosine: nullptr -> 0)
+  const float* rq;   // per query row additive term (euclidean: squared norm; cosine: nullptr -> 1)
+  const float* rg;   // per gallery row additive term (euclidean: squared norm; cosine: nullptr -> 0)
+  const float* sq;   // per query row power-of-two scale (F16X3; 1 otherwise)
+  const float* sg;   // per gallery row power-of-two scale
   float* out;
   int64_t ldo;
   int Q, G;
   int num_kb;        // Dp / 64
-  int nseg;          // 1 (BF16) or 3 (BF16X3)
+  int nseg;          // 1 (BF16) or 3 (F16X3)
   float alpha;       // -2 (euclidean) or -1 (cosine)
   int num_m_tiles, num_n_tiles;
+  uint32_t idesc;    // tcgen05 instruction descriptor (operand format, M, N)
+  int tma_store;     // 1: out is 16-byte aligned with a 16-byte-multiple pitch -> TMA store epilogue
+  int debug;         // ieee_set_debug_flags()
 };
 
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   using Cfg = GemmCfg<CG>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  float* smem_epi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA   (lives in the pair leader for CG == 2)
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA   (per CTA)
   uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue (per CTA)
@@ -84,6 +96,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       tma_prefetch_desc(&tm_a_lo);
       tma_prefetch_desc(&tm_b_lo);
     }
+    if (p.tma_store) tma_prefetch_desc(&tm_out);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) {
@@ -143,7 +156,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only) =====================
     if (is_leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
+      const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -160,7 +173,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+            // advance 16 elements = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
             umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit<CG>(&empty_bar[stage]);                 // smem slot free once these MMAs retire
@@ -173,7 +186,10 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;                       // == warp % 4 -> TMEM lane quarter
-    float* stage_buf = smem_epi + ew * 32 * kStagePitch;
+    uint8_t* my_epi = smem_epi + ew * Cfg::kEpiWarpBytes;
+    float* tile = reinterpret_cast<float*>(my_epi);                          // 1024-byte aligned
+    float* col_rg = reinterpret_cast<float*>(my_epi + Cfg::kEpiTileBytes);   // [256]
+    float* col_sg = col_rg + BLOCK_N;                                        // [256]
     int it = 0;
     for (int t = group_id; t < num_tiles; t += num_groups, ++it) {
       const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
@@ -181,41 +197,78 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + ew * 32;   // first row of this warp
       const int col_tile = n_blk * BLOCK_N;
-      // lane l keeps the row term of row0 + l; broadcast by shuffle in the store loop
-      float rq_lane = 1.0f;
-      if (p.rq != nullptr) rq_lane = (row0 + lane < p.Q) ? p.rq[row0 + lane] : 0.0f;
+      // this thread's row terms (thread <-> TMEM lane <-> output row)
+      const int my_row = row0 + lane;
+      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : 1.0f;
+      const float coef_row = p.alpha * ((p.sq != nullptr && my_row < p.Q) ? p.sq[my_row] : 1.0f);
+      // the tile's column terms, one private copy per warp (no cross-warp barrier needed)
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        const int col = col_tile + j * 32 + lane;
+        col_rg[j * 32 + lane] = (p.rg != nullptr && col < p.G) ? p.rg[col] : 0.0f;
+        col_sg[j * 32 + lane] = (p.sg != nullptr && col < p.G) ? p.sg[col] : 1.0f;
+      }
+      __syncwarp();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (uint32_t(ew * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+        if (!(p.debug & 2)) {
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+        }
         if (c == BLOCK_N / 32 - 1) {
           // all of this thread's accumulator reads are done: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
         }
-        const int col = col_tile + c * 32 + lane;
-        float rg_lane = 0.0f;
-        if (p.rg != nullptr && col < p.G) rg_lane = p.rg[col];
-        __syncwarp();
+        if (col_tile + c * 32 >= p.G || row0 >= p.Q || (p.debug & 1)) continue;   // warp-uniform
+        if (p.tma_store) {
+          // d in registers (thread = row), 16-byte chunks XOR-swizzled by (row & 7) as SWIZZLE_128B expects
+          if (lane == 0) tma_store_wait_read<0>();     // the previous store has finished reading `tile`
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stage_buf[lane * kStagePitch + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        if (col_tile + c * 32 < p.G) {
+          for (int k = 0; k < 8; ++k) {
+            float4 o;
+            const float4 g4 = *reinterpret_cast<const float4*>(col_rg + c * 32 + 4 * k);
+            const float4 s4 = *reinterpret_cast<const float4*>(col_sg + c * 32 + 4 * k);
+            o.x = __fmaf_rn(coef_row * s4.x, __uint_as_float(v[4 * k + 0]), __fadd_rn(rq_row, g4.x));
+            o.y = __fmaf_rn(coef_row * s4.y, __uint_as_float(v[4 * k + 1]), __fadd_rn(rq_row, g4.y));
+            o.z = __fmaf_rn(coef_row * s4.z, __uint_as_float(v[4 * k + 2]), __fadd_rn(rq_row, g4.z));
+            o.w = __fmaf_rn(coef_row * s4.w, __uint_as_float(v[4 * k + 3]), __fadd_rn(rq_row, g4.w));
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tile) + lane * 128 + ((k ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, tile, col_tile + c * 32, row0);
+            tma_store_commit();
+          }
+        } else {
+          // transpose through smem so that a warp writes 32 consecutive columns of one row per instruction
+          const int col = col_tile + c * 32 + lane;
+          const float rg_lane = col_rg[c * 32 + lane], sg_lane = col_sg[c * 32 + lane];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile[lane * kStagePitch + j] = __uint_as_float(v[j]);
+          __syncwarp();
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const float rq = __shfl_sync(0xffffffffu, rq_lane, r);
-            const float a = stage_buf[r * kStagePitch + lane];
+            const float rq = __shfl_sync(0xffffffffu, rq_row, r);
+            const float cf = __shfl_sync(0xffffffffu, coef_row, r);
+            const float a = tile[r * kStagePitch + lane];
             const int row = row0 + r;
             if (row < p.Q && col < p.G)
-              p.out[(int64_t)row * p.ldo + col] = __fmaf_rn(p.alpha, a, __fadd_rn(rq, rg_lane));
+              p.out[(int64_t)row * p.ldo + col] = __fmaf_rn(cf * sg_lane, a, __fadd_rn(rq, rg_lane));
           }
         }
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();   // all bulk stores complete before smem goes away
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -240,22 +293,24 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 plane [rows, Dp] row-major -> tiles of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds.
-static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t Dp, int box_rows) {
+// row-major [rows, cols] matrix of `esize`-byte elements -> tiles of box_rows x box_cols, 128-byte swizzle
+// (box_cols * esize == 128), zero fill / clipping out of bounds.
+static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
+                     int64_t pitch_elems, int box_rows, int box_cols) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return IEEE_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld Dp=%lld)", (int)r, (long long)rows, (long long)Dp);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld pitch=%lld)", (int)r, (long long)rows,
+              (long long)cols, (long long)pitch_elems);
     return IEEE_ERR_CUDA;
   }
   return IEEE_OK;
@@ -268,13 +323,14 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
   const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
   const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const CUtensorMapDataType dt16 = CU_TENSOR_MAP_DATA_TYPE_UINT16;   // the copy engine only moves 16-bit words
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
   int rc;
-  if ((rc = make_tmap(&ta_hi, qb + lq.hi_off, Q, lq.Dp, BLOCK_M))) return rc;
-  if ((rc = make_tmap(&tb_hi, gb + lg.hi_off, G, lg.Dp, Cfg::kBRows))) return rc;
-  if (precision == IEEE_PREC_BF16X3) {
-    if ((rc = make_tmap(&ta_lo, qb + lq.lo_off, Q, lq.Dp, BLOCK_M))) return rc;
-    if ((rc = make_tmap(&tb_lo, gb + lg.lo_off, G, lg.Dp, Cfg::kBRows))) return rc;
+  if ((rc = make_tmap(&ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
+  if (precision == IEEE_PREC_F16X3) {
+    if ((rc = make_tmap(&ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
@@ -283,15 +339,25 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   const bool euclid = metric == IEEE_METRIC_EUCLIDEAN;
   p.rq = euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr;
   p.rg = euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr;
+  p.sq = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(qb + lq.scale_off) : nullptr;
+  p.sg = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(gb + lg.scale_off) : nullptr;
   p.alpha = euclid ? -2.0f : -1.0f;
   p.out = out;
   p.ldo = ldo;
   p.Q = (int)Q;
   p.G = (int)G;
   p.num_kb = (int)(lq.Dp / BLOCK_K);
-  p.nseg = precision == IEEE_PREC_BF16X3 ? 3 : 1;
+  p.nseg = precision == IEEE_PREC_F16X3 ? 3 : 1;
   p.num_m_tiles = (int)((Q + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
+  p.idesc = umma_idesc_16bit(BLOCK_M * CG, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
+  p.debug = g_debug_flags;
+  p.tma_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 && !(g_debug_flags & 4)) ? 1 : 0;
+  if (p.tma_store) {
+    if ((rc = make_tmap(&t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, Q, G, ldo, 32, 32))) return rc;
+  } else {
+    t_out = ta_hi;
+  }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   int groups = sm_count() / CG;
   if (groups > num_tiles) groups = num_tiles;
@@ -313,7 +379,7 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, t_out, p));
   count_launch();
   return IEEE_OK;
 }

@@ -2,7 +2,9 @@
 //
 // Covers torchreid/engine/engine.py:391-394 (optional F.normalize of both sets), the row-norm terms of
 // torchreid/metrics/distance.py:59-61 (pow(2).sum(1)) and the F.normalize calls of distance.py:77-78
-// (x / max(||x||_2, 1e-12)), fused with the fp32 -> bf16 hi/lo split the tensor-core kernel needs.
+// (x / max(||x||_2, 1e-12)), fused with the fp32 -> fp16 hi/lo split (or bf16 rounding) the tensor-core kernel needs.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ieee {
@@ -31,36 +33,60 @@ struct RowLoader<__nv_bfloat16, 1> {
   __device__ static void load(const __nv_bfloat16* p, int64_t i, float (&v)[1]) { v[0] = __bfloat162float(p[i]); }
 };
 
-enum PackMode { PACK_BF16 = 0, PACK_BF16_HILO = 1, PACK_F32 = 2 };
+enum PackMode { PACK_BF16 = 0, PACK_F16_HILO = 1, PACK_F32 = 2 };
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 
 // One warp per row.  n_norm = how many times the row is L2-normalised before the metric sees it: engine
 // normalize_feature (engine.py:391-394) and/or cosine's own F.normalize (distance.py:77-78).  Normalising twice
 // is not the identity in fp32, so the reference's sequence of divisions is reproduced, not collapsed.
+//
+// PACK_F16_HILO: y = x * 2^-e with e chosen per row so that max|y| is in [0.5, 1) (exact scaling), then
+// hi = fp16(y), lo = fp16(y - hi): 22 mantissa bits survive and both planes sit in fp16's normal range for
+// every element within 2^-13 of the row maximum.  The contraction's epilogue multiplies by 2^(e_q + e_g).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
-                                                         int n_norm, int mode, __nv_bfloat16* __restrict__ hi,
-                                                         __nv_bfloat16* __restrict__ lo, float* __restrict__ f32,
-                                                         float* __restrict__ norms) {
+                                                         int n_norm, int mode, uint16_t* __restrict__ hi,
+                                                         uint16_t* __restrict__ lo, float* __restrict__ f32,
+                                                         float* __restrict__ norms, float* __restrict__ row_scale) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* xr = x + row * ld;
   float den[2] = {1.0f, 1.0f};
-  for (int pass = 0; pass < n_norm; ++pass) {
-    float s = 0.f;
-    for (int i = lane * VEC; i < D; i += 32 * VEC) {
-      float v[VEC];
-      RowLoader<T, VEC>::load(xr, i, v);
+  float amax = 0.f;
+  if (n_norm > 0 || mode == PACK_F16_HILO) {
+    for (int pass = 0; pass < (n_norm > 0 ? n_norm : 1); ++pass) {
+      float s = 0.f;
+      for (int i = lane * VEC; i < D; i += 32 * VEC) {
+        float v[VEC];
+        RowLoader<T, VEC>::load(xr, i, v);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float t = v[j];
-        if (pass == 1) t = __fdiv_rn(t, den[0]);
-        s = __fmaf_rn(t, t, s);
+        for (int j = 0; j < VEC; ++j) {
+          float t = v[j];
+          if (pass == 0) amax = fmaxf(amax, fabsf(t));
+          if (pass == 1) t = __fdiv_rn(t, den[0]);
+          s = __fmaf_rn(t, t, s);
+        }
       }
+      s = warp_sum(s);
+      if (pass < n_norm) den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);  // F.normalize: clamp_min(norm, eps)
     }
-    s = warp_sum(s);
-    den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);  // F.normalize: clamp_min(norm, eps)
+    amax = warp_max(amax);
+    // division by a positive constant is monotone, so the maximum of the normalised row is the normalised maximum
+    if (n_norm >= 1) amax = __fdiv_rn(amax, den[0]);
+    if (n_norm >= 2) amax = __fdiv_rn(amax, den[1]);
   }
+  int e = 0;
+  if (mode == PACK_F16_HILO && amax > 0.f && amax < 3.0e38f) {
+    (void)frexpf(amax, &e);          // amax = m * 2^e, m in [0.5, 1)
+    e = max(-100, min(100, e));
+  }
+  const float down = ldexpf(1.0f, -e);   // exact power of two
   float sq = 0.f;
   for (int i = lane * VEC; i < Dp; i += 32 * VEC) {
     float v[VEC];
@@ -70,17 +96,24 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
 #pragma unroll
       for (int j = 0; j < VEC; ++j) v[j] = 0.f;
     }
-    __nv_bfloat16 h[VEC], l[VEC];
+    uint16_t h[VEC], l[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float t = v[j];
       if (n_norm >= 1) t = __fdiv_rn(t, den[0]);
       if (n_norm >= 2) t = __fdiv_rn(t, den[1]);
-      h[j] = __float2bfloat16_rn(t);
-      const float hf = __bfloat162float(h[j]);
-      l[j] = __float2bfloat16_rn(t - hf);
-      // the row term must describe the numbers the contraction actually multiplies
-      const float u = (mode == PACK_BF16) ? hf : t;
+      float u = t;   // the value whose square enters the row term: what the contraction actually multiplies
+      if (mode == PACK_BF16) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(t);
+        h[j] = __bfloat16_as_ushort(b);
+        l[j] = 0;
+        u = __bfloat162float(b);
+      } else if (mode == PACK_F16_HILO) {
+        const float y = t * down;
+        const __half hh = __float2half_rn(y);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn(y - __half2float(hh)));
+      }
       sq = __fmaf_rn(u, u, sq);
       v[j] = t;
     }
@@ -91,15 +124,18 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
     } else {
       if constexpr (VEC == 4) {
         *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
-        if (mode == PACK_BF16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
+        if (mode == PACK_F16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
       } else {
         hi[o] = h[0];
-        if (mode == PACK_BF16_HILO) lo[o] = l[0];
+        if (mode == PACK_F16_HILO) lo[o] = l[0];
       }
     }
   }
   sq = warp_sum(sq);
-  if (lane == 0) norms[row] = sq;
+  if (lane == 0) {
+    norms[row] = sq;
+    row_scale[row] = ldexpf(1.0f, e);
+  }
 }
 
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
@@ -110,29 +146,30 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
   IEEE_REQUIRE(D <= (1 << 24), "pack_features: feature dim too large");
   IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "pack_features: unknown dtype %d", dtype);
   IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
-  IEEE_REQUIRE(precision >= IEEE_PREC_BF16X3 && precision <= IEEE_PREC_FP32_SIMT, "unknown precision %d", precision);
+  IEEE_REQUIRE(precision >= IEEE_PREC_F16X3 && precision <= IEEE_PREC_FP32_SIMT, "unknown precision %d", precision);
   if (rows == 0) return IEEE_OK;
   PackedLayout L = packed_layout(rows, D, precision);
   uint8_t* base = static_cast<uint8_t*>(packed);
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 255) == 0, "pack_features: packed buffer must be 256-byte aligned");
-  auto* hi = reinterpret_cast<__nv_bfloat16*>(base + L.hi_off);
-  auto* lo = reinterpret_cast<__nv_bfloat16*>(base + L.lo_off);
+  auto* hi = reinterpret_cast<uint16_t*>(base + L.hi_off);
+  auto* lo = reinterpret_cast<uint16_t*>(base + L.lo_off);
   auto* f32 = reinterpret_cast<float*>(base);
   auto* norms = reinterpret_cast<float*>(base + L.norm_off);
+  auto* rscale = reinterpret_cast<float*>(base + L.scale_off);
   const int n_norm = (normalize ? 1 : 0) + (metric == IEEE_METRIC_COSINE ? 1 : 0);
-  const int mode = precision == IEEE_PREC_FP32_SIMT ? PACK_F32 : (precision == IEEE_PREC_BF16X3 ? PACK_BF16_HILO : PACK_BF16);
+  const int mode = precision == IEEE_PREC_FP32_SIMT ? PACK_F32 : (precision == IEEE_PREC_F16X3 ? PACK_F16_HILO : PACK_BF16);
   const int warps = 8;
   dim3 grid((unsigned)((rows + warps - 1) / warps)), block(warps * 32);
   if (dtype == IEEE_DTYPE_F32) {
     const float* xf = static_cast<const float*>(x);
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xf) & 15) == 0);
     if (vec)
-      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
     else
-      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
   } else {
     pack_rows_kernel<__nv_bfloat16, 1><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, (int)D,
-                                                                   (int)L.Dp, n_norm, mode, hi, lo, f32, norms);
+                                                                   (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
   }
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());

@@ -65,26 +65,32 @@ size_t gallery_group_bytes(int64_t G) {
   return align256(size_t(Gp) * 8) + align256(size_t(Gp) * 4);
 }
 
-constexpr int kSortChunk = 2048;
+constexpr int kSortChunk = 8192;   // (pid, idx) pairs sorted per CTA in shared memory: 96 KB
 
 __device__ __forceinline__ bool pair_greater(int64_t pa, int32_t ia, int64_t pb, int32_t ib) {
   return pa > pb || (pa == pb && ia > ib);
 }
 
-__global__ void group_init_kernel(const int64_t* __restrict__ g_pids, int64_t G, int64_t Gp, int64_t* pids, int32_t* idx) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Gp) return;
-  pids[i] = i < G ? g_pids[i] : INT64_MAX;
-  idx[i] = i < G ? (int32_t)i : INT32_MAX;   // padding sorts after every real entry of the same pid
-}
-
-// k_start = 2 : full sort of each chunk (all k <= chunk).  k_start = k > chunk : the j < chunk tail of merge step k.
-__global__ void __launch_bounds__(1024) group_sort_local_kernel(int64_t* pids, int32_t* idx, int64_t Gp, int64_t k_start) {
-  __shared__ int64_t sp[kSortChunk];
-  __shared__ int32_t si[kSortChunk];
+// k_start == 2 : load the raw ids (fused initialisation: entry i = (g_pids[i], i), padding sorts last) and fully
+//                sort each chunk (all k <= chunk).
+// k_start  > 2 : the j < chunk tail of merge step k = k_start on already initialised arrays.
+__global__ void __launch_bounds__(1024) group_sort_local_kernel(const int64_t* __restrict__ g_pids, int64_t G, int64_t* pids,
+                                                                 int32_t* idx, int64_t Gp, int64_t k_start) {
+  extern __shared__ __align__(16) uint8_t gs_raw[];
+  int64_t* sp = reinterpret_cast<int64_t*>(gs_raw);
+  int32_t* si = reinterpret_cast<int32_t*>(sp + kSortChunk);
   const int64_t base = (int64_t)blockIdx.x * kSortChunk;
   const int n = (int)min((int64_t)kSortChunk, Gp - base);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { sp[i] = pids[base + i]; si[i] = idx[base + i]; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t gi = base + i;
+    if (k_start == 2) {
+      sp[i] = gi < G ? g_pids[gi] : INT64_MAX;
+      si[i] = gi < G ? (int32_t)gi : INT32_MAX;
+    } else {
+      sp[i] = pids[gi];
+      si[i] = idx[gi];
+    }
+  }
   const int64_t k_end = (k_start == 2) ? n : k_start;
   for (int64_t k = k_start; k <= k_end; k <<= 1) {
     int j0 = (int)min(k >> 1, (int64_t)(n >> 1));
@@ -122,15 +128,22 @@ int gallery_group(const int64_t* g_pids, int64_t G, void* blob, cudaStream_t str
   IEEE_REQUIRE(g_pids && blob && G > 0 && G < (int64_t(1) << 31), "gallery_group: bad arguments (G=%lld)", (long long)G);
   GroupView v = group_view(blob, G);
   const int threads = 256;
-  group_init_kernel<<<(unsigned)((v.Gp + threads - 1) / threads), threads, 0, stream>>>(g_pids, G, v.Gp, v.pids, v.idx); count_launch();
+  const size_t smem = size_t(kSortChunk) * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(group_sort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   const unsigned chunks = (unsigned)((v.Gp + kSortChunk - 1) / kSortChunk);
-  group_sort_local_kernel<<<chunks, 1024, 0, stream>>>(v.pids, v.idx, v.Gp, 2); count_launch();
+  group_sort_local_kernel<<<chunks, 1024, smem, stream>>>(g_pids, G, v.pids, v.idx, v.Gp, 2);
+  count_launch();
   for (int64_t k = 2 * (int64_t)kSortChunk; k <= v.Gp; k <<= 1) {
     for (int64_t j = k >> 1; j >= kSortChunk; j >>= 1) {
       group_sort_global_kernel<<<(unsigned)((v.Gp + threads - 1) / threads), threads, 0, stream>>>(v.pids, v.idx, v.Gp, j, k);
       count_launch();
     }
-    group_sort_local_kernel<<<chunks, 1024, 0, stream>>>(v.pids, v.idx, v.Gp, k); count_launch();
+    group_sort_local_kernel<<<chunks, 1024, smem, stream>>>(g_pids, G, v.pids, v.idx, v.Gp, k);
+    count_launch();
   }
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -217,22 +230,24 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------------------
 // count: one CTA per query; single streaming pass over the local distance row.
+//
+// Every distance is binned against the query's sorted thresholds T_0 < ... < T_{R-1} (the relevant items' packed
+// (distance key, global index)): b(e) = #{k : T_k <lex e}.  A 1024-cell table over [d(T_0), d(T_{R-1})] maps a
+// distance to its bin with one multiply and one shared-memory load; only cells that contain a threshold need
+// exact 64-bit compares.  Bin counters are PRIVATE per thread (16-bit, layout [bin][thread]: conflict-free plain
+// read-modify-write, no atomics) and are summed once after the stream; queries with more relevant items than
+// the private table can hold fall back to shared atomics.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kCountThreads = 256;
 constexpr int kLutCells = 1024;
+constexpr int kPrivateBinBudget = 96 * 1024;   // bytes of private counters per CTA ((R + 1) * 512 B)
 
-struct CountSmem {       // dynamic smem carve: T[Rp] u64 | hist[Rp + 1] i32 | cell_start[L] | cell_cnt[L] | misc
-  uint64_t* T;
-  int32_t* hist;
-  int32_t* cell_start;
-  int32_t* cell_cnt;
-  int32_t* misc;
-};
-__host__ __device__ inline size_t count_smem_bytes(int Rp) {
-  return size_t(Rp) * 8 + size_t(Rp + 1 + 2 * kLutCells + 64) * 4;
+__host__ __device__ inline size_t count_smem_bytes(int Rp, bool priv) {
+  // T[Rp] u64 | hist[Rp + 1] i32 | cell[L] u32 | misc[64] i32 | priv[(Rp + 1) * threads] u16
+  return size_t(Rp) * 8 + size_t(Rp + 1 + kLutCells + 64) * 4 + (priv ? size_t(Rp + 1) * kCountThreads * 2 : 0);
 }
 
-// b(e) = #{k : T_k <lex e}; `same` = #{k : key(T_k) == key(e)}; is_thr = e is itself a threshold
+// b(e) = lo + #{k in [lo, lo+n) : T_k <lex e}; `same` = #{k : key(T_k) == key(e)}; is_thr = e is itself a threshold
 __device__ __forceinline__ int exact_bin(const uint64_t* T, int lo, int n, uint64_t pe, int& same, bool& is_thr) {
   int b = lo;
   const uint32_t ke = (uint32_t)(pe >> 32);
@@ -245,6 +260,7 @@ __device__ __forceinline__ int exact_bin(const uint64_t* T, int lo, int n, uint6
   return b;
 }
 
+template <bool kPrivate>
 __global__ void __launch_bounds__(kCountThreads)
 rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
                   int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
@@ -253,9 +269,9 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   extern __shared__ __align__(16) uint8_t cs_raw[];
   uint64_t* T = reinterpret_cast<uint64_t*>(cs_raw);
   int32_t* hist = reinterpret_cast<int32_t*>(cs_raw + size_t(Rp) * 8);
-  int32_t* cell_start = hist + Rp + 1;
-  int32_t* cell_cnt = cell_start + kLutCells;
-  int32_t* misc = cell_cnt + kLutCells;   // [0] R, [1] ties (signed), [2..] scan scratch
+  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + Rp + 1);     // first bin of the cell | (#thresholds in it) << 20
+  int32_t* misc = reinterpret_cast<int32_t*>(cell + kLutCells);    // [0] R, [1] ties (signed), [2..] scan scratch
+  uint16_t* priv = reinterpret_cast<uint16_t*>(misc + 64);         // [(R + 1)][kCountThreads]
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   const int stride = shards * cap + 1;
@@ -264,7 +280,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
   for (int i = tid; i < Rp; i += kCountThreads) T[i] = kPadKey;
   for (int i = tid; i <= Rp; i += kCountThreads) hist[i] = 0;
-  for (int i = tid; i < 2 * kLutCells; i += kCountThreads) cell_start[i] = 0;
+  for (int i = tid; i < kLutCells; i += kCountThreads) cell[i] = 0;
   if (tid == 0) { misc[0] = 0; misc[1] = 0; }
   __syncthreads();
   for (int s = 0; s < shards; ++s) {
@@ -280,26 +296,31 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   const int nj = n_junk[q];
   if (tid == 0) out[stride - 1] = nj;
   if (R == 0) return;   // invalid query (rank.py:142-144): nothing to rank against
-  block_bitonic_sort(T, Rp);
+  block_bitonic_sort(T, next_pow2(max(R, 2)));
+  if constexpr (kPrivate) {
+    uint32_t* pz = reinterpret_cast<uint32_t*>(priv);
+    for (int i = tid; i < (R + 1) * kCountThreads / 2; i += kCountThreads) pz[i] = 0;
+  }
 
   // ---- cell table over [lo, hi] of the threshold distances ----------------------------------------------
   const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
-  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
+  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f &&
+                       isfinite((float)kLutCells / span) && R < (1 << 11);
   const float scale = use_lut ? (float)kLutCells / span : 0.f;
   if (use_lut) {
     for (int k = tid; k < R; k += kCountThreads) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
       const int c = min((int)((d - lo) * scale), kLutCells - 1);
-      atomicAdd(&cell_cnt[c], 1);
+      atomicAdd(&cell[c], 1u << 20);
     }
     __syncthreads();
-    // exclusive scan of cell_cnt -> cell_start (kLutCells == 4 * kCountThreads)
+    // exclusive scan of the per-cell counts -> first bin of each cell (kLutCells == 4 * kCountThreads)
     {
       int v[4], sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[j] = cell_cnt[tid * 4 + j]; sum += v[j]; }
+      for (int j = 0; j < 4; ++j) { v[j] = (int)(cell[tid * 4 + j] >> 20); sum += v[j]; }
       int incl = sum;
       const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -311,7 +332,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
       for (int i = 0; i < w; ++i) woff += wsum[i];
       int run = woff + incl - sum;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { cell_start[tid * 4 + j] = run; run += v[j]; }
+      for (int j = 0; j < 4; ++j) { cell[tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
     }
   }
   __syncthreads();
@@ -320,25 +341,47 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   const float* row = distmat + q * ld;
   int c_before = 0;      // elements before every threshold (bin 0), kept in a register
   int tie_local = 0;
-  auto visit = [&](float d, int64_t g) {
+  // 16-bit slot of this thread inside a bin's 256 counters: 32-bit word = lane + 32 * (warp & 3), half = warp >> 2,
+  // so the 32 lanes of a warp always touch 32 different banks whatever their bins are
+  const int priv_slot = (((tid & 31) + 32 * ((tid >> 5) & 3)) << 1) | (tid >> 7);
+  auto bump = [&](int b) {
+    if constexpr (kPrivate) {
+      uint16_t* p16 = priv + b * kCountThreads + priv_slot;
+      *p16 = (uint16_t)(*p16 + 1);
+      if (*p16 == 0xFFFFu) { atomicAdd(&hist[b], 0xFFFF); *p16 = 0; }   // spill before the counter can wrap
+    } else {
+      atomicAdd(&hist[b], 1);
+    }
+  };
+  auto visit_slow = [&](float d, int64_t g) {      // non-finite / degenerate thresholds: search all of T
     const uint32_t ke = order_key(d);
-    if (ke > kmax) return;                         // after every threshold: moves no position
+    if (ke > kmax) return;
     if (ke < kmin) { ++c_before; return; }
     const uint64_t pe = (uint64_t(ke) << 32) | (uint32_t)(g + g_offset);
-    int b, same = 0;
+    int a = 0, e = R;
+    while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
+    int same = 0;
     bool is_thr = false;
-    if (use_lut) {
-      const int c = min((int)((d - lo) * scale), kLutCells - 1);
-      b = exact_bin(T, cell_start[c], cell_cnt[c], pe, same, is_thr);
-    } else {                                       // degenerate / non-finite thresholds: search all of T
-      int a = 0, e = R;
-      while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
-      b = a;
-      for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) { same++; is_thr |= (T[j] == pe); }
-      for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) same++;
-    }
+    for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) { same++; is_thr |= (T[j] == pe); }
+    for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) same++;
     if (!is_thr) tie_local += same;
-    atomicAdd(&hist[b], 1);
+    bump(a);
+  };
+  auto visit = [&](float d, int64_t g) {
+    if (!use_lut) { visit_slow(d, g); return; }
+    // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
+    if (!(d <= hi)) return;                        // after every threshold: moves no position
+    if (d < lo) { ++c_before; return; }
+    const uint32_t ce = cell[min((int)((d - lo) * scale), kLutCells - 1)];
+    int b = (int)(ce & 0xFFFFFu);
+    if (ce >> 20) {                                // the cell holds thresholds: exact (key, index) compares
+      const uint64_t pe = pack_key(d, (uint32_t)(g + g_offset));
+      int same = 0;
+      bool is_thr = false;
+      b = exact_bin(T, b, (int)(ce >> 20), pe, same, is_thr);
+      if (!is_thr) tie_local += same;
+    }
+    bump(b);
   };
   {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
@@ -366,6 +409,18 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
       visit(a.x, g0); visit(a.y, g0 + 1); visit(a.z, g0 + 2); visit(a.w, g0 + 3);
     }
     for (int64_t g = head + 4 * nvec + tid; g < G; g += kCountThreads) visit(row[g], g);
+  }
+  __syncthreads();
+  if constexpr (kPrivate) {   // fold the private counters: warp w sums bins w, w + 8, ...
+    const int lane = tid & 31, w = tid >> 5;
+    for (int b = w; b <= R; b += kCountThreads / 32) {
+      int sum = 0;
+#pragma unroll
+      for (int j = 0; j < kCountThreads / 32; ++j) sum += priv[b * kCountThreads + j * 32 + lane];
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0 && sum) atomicAdd(&hist[b], sum);
+    }
+    __syncthreads();
   }
   // ---- junk items were streamed like everything else: take them out again (rank.py:136-140) -------------
   for (int i = tid; i < nj; i += kCountThreads) {
@@ -415,7 +470,11 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   if (tid == 0 && ties_out != nullptr && misc[1] != 0) atomicAdd(ties_out, (unsigned long long)(long long)misc[1]);
 }
 
-size_t rank_count_smem(int shards, int cap) { return count_smem_bytes(next_pow2(max(shards * cap, 2))); }
+static inline bool count_use_private(int Rp) { return size_t(Rp + 1) * kCountThreads * 2 <= size_t(kPrivateBinBudget); }
+size_t rank_count_smem(int shards, int cap) {
+  const int Rp = next_pow2(max(shards * cap, 2));
+  return count_smem_bytes(Rp, count_use_private(Rp));
+}
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
                const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
@@ -424,16 +483,25 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   IEEE_REQUIRE(Q >= 0 && G > 0 && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
   const int Rp = next_pow2(max(shards * cap, 2));
-  const size_t smem = count_smem_bytes(Rp);
+  const bool priv = count_use_private(Rp);
+  const size_t smem = count_smem_bytes(Rp, priv);
   IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: shards*cap=%d relevant items per query exceed the shared-memory budget",
                shards * cap);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > smem_set[priv]) {
+    if (priv)
+      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[priv] = smem;
   }
-  rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, G, g_offset, shards, cap, Rp, rel_all,
-                                                                  n_rel_all, junk, n_junk, counts, ties); count_launch();
+  if (priv)
+    rank_count_kernel<true><<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, G, g_offset, shards, cap, Rp, rel_all,
+                                                                          n_rel_all, junk, n_junk, counts, ties);
+  else
+    rank_count_kernel<false><<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, G, g_offset, shards, cap, Rp, rel_all,
+                                                                           n_rel_all, junk, n_junk, counts, ties);
+  count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }

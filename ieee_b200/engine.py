@@ -69,7 +69,7 @@ class RetrievalEvaluator:
             raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(dist_metric))
         self.device = gf.device
         self.metric, self.normalize = dist_metric, normalize_feature
-        self.precision = precision or ("bf16" if gf.dtype == torch.bfloat16 else "bf16x3")
+        self.precision = precision or ("bf16" if gf.dtype == torch.bfloat16 else "f16x3")
         self.max_rank = max_rank
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
@@ -125,7 +125,10 @@ class RetrievalEvaluator:
             ties = torch.zeros(1, dtype=torch.int64, device=self.device)
             rows = self._block_rows(Q)
             if self._block is None or self._block.shape[0] < rows:
-                self._block = torch.empty((rows, self.G), dtype=torch.float32, device=self.device)
+                # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
+                # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
+                pitch = (self.G + 31) // 32 * 32
+                self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
             full = None
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)

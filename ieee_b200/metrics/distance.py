@@ -9,8 +9,8 @@ import torch
 
 from .. import _lib
 
-# fp32 inputs default to the fp32-equivalent bf16x3 split; bf16 inputs multiply exactly in one bf16 pass
-DEFAULT_PRECISION = {torch.float32: "bf16x3", torch.bfloat16: "bf16"}
+# fp32 inputs default to the fp32-equivalent f16x3 split; bf16 inputs multiply exactly in one bf16 pass
+DEFAULT_PRECISION = {torch.float32: "f16x3", torch.bfloat16: "bf16"}
 
 
 def _device_distmat(a: torch.Tensor, b: torch.Tensor, metric: str, normalize: bool = False, precision: str | None = None,
@@ -45,7 +45,7 @@ def compute_distance_matrix(input1, input2, metric="euclidean", precision=None):
         input1 (torch.Tensor): 2-D feature matrix.
         input2 (torch.Tensor): 2-D feature matrix.
         metric (str, optional): "euclidean" or "cosine". Default is "euclidean".
-        precision (str, optional): "bf16x3" (fp32-equivalent, default for float32), "bf16", "fp32_simt".
+        precision (str, optional): "f16x3" (fp32-equivalent, default for float32), "bf16", "fp32_simt".
 
     Returns:
         torch.Tensor: distance matrix, same dtype and device as the inputs.

@@ -53,19 +53,23 @@ typedef enum { IEEE_METRIC_EUCLIDEAN = 0, IEEE_METRIC_COSINE = 1 } ieee_metric; 
 typedef enum { IEEE_DTYPE_F32 = 0, IEEE_DTYPE_BF16 = 1 } ieee_dtype;
 
 /* Arithmetic of the distance contraction (always fp32 accumulation in TMEM / registers):
- *   BF16X3    fp32 features split into bf16 hi+lo, three tcgen05 MMAs per k-step (hi*hi, hi*lo, lo*hi):
- *             fp32-equivalent products; the mode that meets the 1e-4 parity bound for fp32 inputs.
- *   BF16      one tcgen05 MMA per k-step on bf16-rounded features (exact for bf16 inputs).
+ *   F16X3     fp32 features scaled per row by a power of two, split into fp16 hi + lo (22 mantissa bits), three
+ *             tcgen05 MMAs per k-step (hi*hi, hi*lo, lo*hi) into one accumulator; the dropped lo*lo term is
+ *             <= 2^-24 relative: fp32-grade products.  Default for fp32 inputs; meets the 1e-4 parity bound.
+ *   BF16      one tcgen05 MMA per k-step on bf16-rounded features (exact products for bf16 inputs).
  *   FP32_SIMT plain fp32 FMA kernel (no tensor cores); cross-check for the tensor path.           */
-typedef enum { IEEE_PREC_BF16X3 = 0, IEEE_PREC_BF16 = 1, IEEE_PREC_FP32_SIMT = 2 } ieee_precision;
+typedef enum { IEEE_PREC_F16X3 = 0, IEEE_PREC_BF16 = 1, IEEE_PREC_FP32_SIMT = 2 } ieee_precision;
 
 const char* ieee_last_error(void);
 int ieee_abi_version(void);
 /* Number of SMs / compute capability (major*10+minor) of the current device; IEEE_ERR_CUDA without one. */
 int ieee_device_info(int* sm_count, int* compute_capability);
-/* Tensor-core kernel pairing: 2 (default) = tcgen05 cta_group::2, one 256 x 256 tile per SM pair;
- * 1 = cta_group::1, one 128 x 256 tile per SM.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
+/* Tensor-core kernel pairing: 1 (default) = tcgen05 cta_group::1, one 128 x 256 tile per SM;
+ * 2 = cta_group::2, one 256 x 256 tile per SM pair.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
 int ieee_set_cta_group(int cta_group);
+/* Diagnostics for kernel tuning (results are WRONG when non-zero): bit 0 = tensor-core epilogue skips its global
+ * stores, bit 1 = epilogue also skips the TMEM reads.  Returns the previous value. */
+int ieee_set_debug_flags(int flags);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
 int64_t ieee_launch_count(void);
 
@@ -74,9 +78,9 @@ int64_t ieee_launch_count(void);
  * squared, unclamped) and distance.py:67-80 (cosine_distance: 1 - normalize(a) normalize(b)^T, eps 1e-12).
  * `normalize` != 0 applies engine.py:391-394 (F.normalize of both sets) first.
  *
- * Packed operand = what the tensor-core kernel consumes: bf16 hi plane (+ lo plane for BF16X3), each
- * [rows, Dp] with Dp = D rounded up to 64, zero padded, plus one fp32 per row (squared norm for
- * euclidean, unused for cosine).  Pack a gallery once, reuse it for every query block.
+ * Packed operand = what the tensor-core kernel consumes: a 16-bit hi plane (+ lo plane for F16X3), each
+ * [rows, Dp] with Dp = D rounded up to 64, zero padded, plus two fp32 per row (squared norm and the
+ * power-of-two row scale).  Pack a gallery once, reuse it for every query block.
  * ---------------------------------------------------------------------------------------------- */
 size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision);
 int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,

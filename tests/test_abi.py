@@ -39,9 +39,9 @@ def test_abi_version_and_struct_layout():
 
 def test_size_queries_need_no_gpu():
     lib = _lib.load()
-    # hi + lo planes of [rows, roundup(D,64)] bf16 plus one fp32 per row, 256-byte aligned sections
-    assert lib.ieee_packed_bytes(128, 2304, _lib.PRECISIONS["bf16x3"]) == 2 * 128 * 2304 * 2 + 512
-    assert lib.ieee_packed_bytes(128, 100, _lib.PRECISIONS["bf16"]) == 128 * 128 * 2 + 512
+    # hi + lo planes of [rows, roundup(D,64)] 16-bit plus two fp32 per row (norm, scale), 256-byte aligned sections
+    assert lib.ieee_packed_bytes(128, 2304, _lib.PRECISIONS["f16x3"]) == 2 * 128 * 2304 * 2 + 1024
+    assert lib.ieee_packed_bytes(128, 100, _lib.PRECISIONS["bf16"]) == 128 * 128 * 2 + 1024
     assert lib.ieee_gallery_group_bytes(15913) == 16384 * 12
     assert lib.ieee_rank_finalize_workspace_bytes(1000) > 0
 
