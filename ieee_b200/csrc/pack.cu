@@ -45,9 +45,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // normalize_feature (engine.py:391-394) and/or cosine's own F.normalize (distance.py:77-78).  Normalising twice
 // is not the identity in fp32, so the reference's sequence of divisions is reproduced, not collapsed.
 //
-// PACK_F16_HILO: y = x * 2^-e with e chosen per row so that max|y| is in [0.5, 1) (exact scaling), then
-// hi = fp16(y), lo = fp16(y - hi): 22 mantissa bits survive and both planes sit in fp16's normal range for
-// every element within 2^-13 of the row maximum.  The contraction's epilogue multiplies by 2^(e_q + e_g).
+// PACK_F16_HILO: y = x * 2^(14-e) with e chosen per row so that max|y| is in [2^13, 2^14) (exact scaling, below
+// fp16's 65504), then hi = fp16(y), lo = fp16(y - hi): 22 mantissa bits survive, and lo (~2^-12 |y|) stays a
+// NORMAL fp16 number for every element within 2^-16 of the row maximum.  The contraction's epilogue multiplies
+// by 2^(e_q - 14) * 2^(e_g - 14).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
                                                          int n_norm, int mode, uint16_t* __restrict__ hi,
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   int e = 0;
   if (mode == PACK_F16_HILO && amax > 0.f && amax < 3.0e38f) {
     (void)frexpf(amax, &e);          // amax = m * 2^e, m in [0.5, 1)
-    e = max(-100, min(100, e));
+    e = max(-100, min(100, e)) - 14;   // y = x * 2^-e has its maximum in [2^13, 2^14)
   }
   const float down = ldexpf(1.0f, -e);   // exact power of two
   float sq = 0.f;

@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kCountThreads = 256;
 constexpr int kLutCells = 1024;
-constexpr int kPrivateBinBudget = 96 * 1024;   // bytes of private counters per CTA ((R + 1) * 512 B)
+constexpr int kPrivateBinBudget = 96 * 1024;   // bytes of private counters per CTA ((R + 2) * 512 B)
 
 __host__ __device__ inline size_t count_smem_bytes(int Rp, bool priv) {
-  // T[Rp] u64 | hist[Rp + 1] i32 | cell[L] u32 | misc[64] i32 | priv[(Rp + 1) * threads] u16
-  return size_t(Rp) * 8 + size_t(Rp + 1 + kLutCells + 64) * 4 + (priv ? size_t(Rp + 1) * kCountThreads * 2 : 0);
+  // T[Rp] u64 | hist[Rp + 2] i32 | cell[L] u32 | misc[64] i32 | priv[(Rp + 2) * threads] u16
+  return size_t(Rp) * 8 + size_t(Rp + 2 + kLutCells + 64) * 4 + (priv ? size_t(Rp + 2) * kCountThreads * 2 : 0);
 }
 
 // b(e) = lo + #{k in [lo, lo+n) : T_k <lex e}; `same` = #{k : key(T_k) == key(e)}; is_thr = e is itself a threshold
@@ -269,7 +269,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   extern __shared__ __align__(16) uint8_t cs_raw[];
   uint64_t* T = reinterpret_cast<uint64_t*>(cs_raw);
   int32_t* hist = reinterpret_cast<int32_t*>(cs_raw + size_t(Rp) * 8);
-  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + Rp + 1);     // first bin of the cell | (#thresholds in it) << 20
+  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + Rp + 2);     // first bin of the cell | (#thresholds in it) << 20
   int32_t* misc = reinterpret_cast<int32_t*>(cell + kLutCells);    // [0] R, [1] ties (signed), [2..] scan scratch
   uint16_t* priv = reinterpret_cast<uint16_t*>(misc + 64);         // [(R + 1)][kCountThreads]
   const int64_t q = blockIdx.x;
@@ -279,7 +279,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
 
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
   for (int i = tid; i < Rp; i += kCountThreads) T[i] = kPadKey;
-  for (int i = tid; i <= Rp; i += kCountThreads) hist[i] = 0;
+  for (int i = tid; i < Rp + 2; i += kCountThreads) hist[i] = 0;
   for (int i = tid; i < kLutCells; i += kCountThreads) cell[i] = 0;
   if (tid == 0) { misc[0] = 0; misc[1] = 0; }
   __syncthreads();
@@ -299,7 +299,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   block_bitonic_sort(T, next_pow2(max(R, 2)));
   if constexpr (kPrivate) {
     uint32_t* pz = reinterpret_cast<uint32_t*>(priv);
-    for (int i = tid; i < (R + 1) * kCountThreads / 2; i += kCountThreads) pz[i] = 0;
+    for (int i = tid; i < (R + 2) * kCountThreads / 2; i += kCountThreads) pz[i] = 0;
   }
 
   // ---- cell table over [lo, hi] of the threshold distances ----------------------------------------------
@@ -339,47 +339,54 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
 
   // ---- stream the row ---------------------------------------------------------------------------------------
   const float* row = distmat + q * ld;
-  int c_before = 0;      // elements before every threshold (bin 0), kept in a register
   int tie_local = 0;
   // 16-bit slot of this thread inside a bin's 256 counters: 32-bit word = lane + 32 * (warp & 3), half = warp >> 2,
   // so the 32 lanes of a warp always touch 32 different banks whatever their bins are
   const int priv_slot = (((tid & 31) + 32 * ((tid >> 5) & 3)) << 1) | (tid >> 7);
+  // Branch-free per-element body (lanes must stay converged across the 16 elements in flight): every element
+  // increments exactly one counter -- bin 0 if it precedes all thresholds, the trash bin R + 1 if it follows them
+  // (or is NaN), else its bin from the cell table; only cells that hold a threshold take a (reconverging) branch.
+  const int trash = R + 1;
+  const bool may_wrap = (G + kCountThreads - 1) / kCountThreads >= 0xFFFF;   // uniform; false below 16.7 M columns
   auto bump = [&](int b) {
     if constexpr (kPrivate) {
       uint16_t* p16 = priv + b * kCountThreads + priv_slot;
-      *p16 = (uint16_t)(*p16 + 1);
-      if (*p16 == 0xFFFFu) { atomicAdd(&hist[b], 0xFFFF); *p16 = 0; }   // spill before the counter can wrap
+      const uint16_t nv = (uint16_t)(*p16 + 1);
+      *p16 = nv;
+      if (may_wrap && nv == 0xFFFFu) { atomicAdd(&hist[b], 0xFFFF); *p16 = 0; }   // spill before the counter can wrap
     } else {
       atomicAdd(&hist[b], 1);
     }
   };
-  auto visit_slow = [&](float d, int64_t g) {      // non-finite / degenerate thresholds: search all of T
-    const uint32_t ke = order_key(d);
-    if (ke > kmax) return;
-    if (ke < kmin) { ++c_before; return; }
-    const uint64_t pe = (uint64_t(ke) << 32) | (uint32_t)(g + g_offset);
-    int a = 0, e = R;
-    while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
-    int same = 0;
-    bool is_thr = false;
-    for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) { same++; is_thr |= (T[j] == pe); }
-    for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) same++;
-    if (!is_thr) tie_local += same;
-    bump(a);
-  };
   auto visit = [&](float d, int64_t g) {
-    if (!use_lut) { visit_slow(d, g); return; }
-    // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
-    if (!(d <= hi)) return;                        // after every threshold: moves no position
-    if (d < lo) { ++c_before; return; }
-    const uint32_t ce = cell[min((int)((d - lo) * scale), kLutCells - 1)];
-    int b = (int)(ce & 0xFFFFFu);
-    if (ce >> 20) {                                // the cell holds thresholds: exact (key, index) compares
-      const uint64_t pe = pack_key(d, (uint32_t)(g + g_offset));
+    int b;
+    if (use_lut) {
+      // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
+      const bool in = d <= hi;
+      const bool before = d < lo;
+      const int ci = max(0, min((int)((d - lo) * scale), kLutCells - 1));
+      const uint32_t ce = cell[ci];
+      b = (int)(ce & 0xFFFFFu);
+      if (in && !before && (ce >> 20)) {           // the cell holds thresholds: exact (key, index) compares
+        const uint64_t pe = pack_key(d, (uint32_t)(g + g_offset));
+        int same = 0;
+        bool is_thr = false;
+        b = exact_bin(T, b, (int)(ce >> 20), pe, same, is_thr);
+        if (!is_thr) tie_local += same;
+      }
+      b = before ? 0 : b;
+      b = in ? b : trash;
+    } else {                                       // non-finite / degenerate thresholds: search all of T
+      const uint32_t ke = order_key(d);
+      const uint64_t pe = (uint64_t(ke) << 32) | (uint32_t)(g + g_offset);
+      int a = 0, e = R;
+      while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
       int same = 0;
       bool is_thr = false;
-      b = exact_bin(T, b, (int)(ce >> 20), pe, same, is_thr);
+      for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) { same++; is_thr |= (T[j] == pe); }
+      for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) same++;
       if (!is_thr) tie_local += same;
+      b = (ke > kmax) ? trash : a;
     }
     bump(b);
   };
@@ -427,21 +434,15 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
     const uint64_t pe = junk[q * cap + i];
     const uint32_t ke = (uint32_t)(pe >> 32);
     if (ke > kmax) continue;
-    if (ke < kmin) { --c_before; continue; }
+    if (ke < kmin) { atomicSub(&hist[0], 1); continue; }
     int a = 0, e = R;
     while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
     for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) tie_local--;
     for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) tie_local--;
     atomicSub(&hist[a], 1);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    c_before += __shfl_xor_sync(0xffffffffu, c_before, o);
-    tie_local += __shfl_xor_sync(0xffffffffu, tie_local, o);
-  }
-  if ((tid & 31) == 0) {
-    if (c_before) atomicAdd(&hist[0], c_before);
-    if (tie_local) atomicAdd(&misc[1], tie_local);
-  }
+  for (int o = 16; o > 0; o >>= 1) tie_local += __shfl_xor_sync(0xffffffffu, tie_local, o);
+  if ((tid & 31) == 0 && tie_local) atomicAdd(&misc[1], tie_local);
   __syncthreads();
   // ---- counts[k] = sum_{b <= k} hist[b] - [T_k is a local row entry (it was binned at b == k)] -----------
   __shared__ int carry;
@@ -470,7 +471,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   if (tid == 0 && ties_out != nullptr && misc[1] != 0) atomicAdd(ties_out, (unsigned long long)(long long)misc[1]);
 }
 
-static inline bool count_use_private(int Rp) { return size_t(Rp + 1) * kCountThreads * 2 <= size_t(kPrivateBinBudget); }
+static inline bool count_use_private(int Rp) { return size_t(Rp + 2) * kCountThreads * 2 <= size_t(kPrivateBinBudget); }
 size_t rank_count_smem(int shards, int cap) {
   const int Rp = next_pow2(max(shards * cap, 2));
   return count_smem_bytes(Rp, count_use_private(Rp));
