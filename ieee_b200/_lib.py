@@ -51,7 +51,7 @@ SIGNATURES = {
     "ieee_topk": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
     "ieee_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
     "ieee_rerank_workspace_bytes": (sz, [i64, i64, i32, i32]),
-    "ieee_rerank": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, f32, vp, i64, vp, sz, vp]),
+    "ieee_rerank": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
 }
 
 _lib = None

@@ -201,7 +201,7 @@ int ieee_topk_merge(const int32_t* idx_all, const float* val_all, int32_t shards
  * ---------------------------------------------------------------------------------------------- */
 size_t ieee_rerank_workspace_bytes(int64_t Q, int64_t G, int32_t k1, int32_t k2);
 int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, const float* g_g, int64_t ld_gg,
-                int64_t Q, int64_t G, int32_t k1, int32_t k2, float lambda_value, float* out, int64_t ldo,
+                int64_t Q, int64_t G, int32_t k1, int32_t k2, double lambda_value, float* out, int64_t ldo,
                 void* workspace, size_t workspace_bytes, ieee_stream_t stream);
 
 #ifdef __cplusplus
