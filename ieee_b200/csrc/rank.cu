@@ -668,8 +668,10 @@ topk_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
       }
     }
     __syncthreads();
-    if (count > kTopkBuf - kTile) {          // next tile could overflow: keep the k best, tighten the threshold
-      const int n = count;
+    const int filled = count;                // snapshot taken between two barriers: every thread sees the same value
+    __syncthreads();                         // (without it fast threads would already be appending the next tile)
+    if (filled > kTopkBuf - kTile) {         // next tile could overflow: keep the k best, tighten the threshold
+      const int n = filled;
       for (int i = n + tid; i < kTopkBuf; i += kTopkThreads) cand[i] = kPadKey;
       block_bitonic_sort(cand, kTopkBuf);
       if (tid == 0) { count = min(n, k); if (n >= k) tau_s = cand[k - 1]; }
