@@ -1,0 +1,100 @@
+"""GPU parity of the gallery-sharded path: the kernels' shard arguments on one GPU, and -- when the box has two
+GPUs -- the real thing over NCCL (one process per GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from ieee_b200 import _lib
+from ieee_b200.engine import RetrievalEvaluator, shard_bounds
+from ieee_b200.metrics.rank import GalleryLabels, RankStages, topk_ranked_list
+from ieee_b200.testing import make_retrieval_set
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_shard_stages_on_one_gpu(shards):
+    """gather / count per shard with global offsets, lists concatenated as the all-gather would, counts summed as the
+    all-reduce would: bit-identical to the unsharded evaluation."""
+    s = make_retrieval_set(150, 1203, 20, 4, dim=64, sigma=2.0, seed=shards)
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    d[:, ::3] = np.round(d[:, ::3])                                  # ties, also across shard boundaries
+    cmc_o, map_o, info = R.eval_market1501(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, 20, return_info=True)
+    dev = torch.device("cuda")
+    Q, G = d.shape
+    qp, qc = torch.from_numpy(s.q_pids).to(dev), torch.from_numpy(s.q_camids).to(dev)
+    parts = []
+    for r in range(shards):
+        g0, g1 = shard_bounds(G, shards, r)
+        dl = torch.from_numpy(np.ascontiguousarray(d[:, g0:g1])).to(dev)
+        parts.append((g0, g1, dl, GalleryLabels(s.g_pids[g0:g1], s.g_camids[g0:g1], dev)))
+    cap = max(p[3].list_cap(qp) for p in parts)
+    stages = [RankStages(Q, cap, shards, dev) for _ in parts]
+    for st, (g0, g1, dl, gal) in zip(stages, parts):
+        st.gather(dl, qp, qc, gal, g0)
+    rel_all = torch.stack([st.rel for st in stages]).contiguous()
+    n_rel_all = torch.stack([st.n_rel for st in stages]).contiguous()
+    for st, (g0, g1, dl, gal) in zip(stages, parts):
+        st.count(dl, g1 - g0, g0, rel_all, n_rel_all)
+    total = torch.stack([st.counts for st in stages]).sum(0).to(torch.int32).contiguous()
+    ties = torch.stack([st.flags[1:2] for st in stages]).sum(0).contiguous()
+    fin = stages[0]
+    fin.finalize(G, 20, n_rel_all=n_rel_all, counts=total, ties=ties)
+    summary = fin.read_summary()
+    assert np.array_equal(fin.cmc.cpu().numpy(), cmc_o) and abs(summary.mAP - map_o) < 1e-9
+    assert np.array_equal(fin.first.cpu().numpy(), info["first_hit"])
+
+
+def test_topk_merge_across_shards():
+    s = make_retrieval_set(64, 1000, 16, 3, dim=64, sigma=2.0, seed=1)
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    d[:, ::4] = np.round(d[:, ::4])
+    k, shards = 20, 4
+    idx_o, val_o = R.topk_kept(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, k)
+    idx_parts, val_parts = [], []
+    for r in range(shards):
+        g0, g1 = shard_bounds(d.shape[1], shards, r)
+        i, v = topk_ranked_list(np.ascontiguousarray(d[:, g0:g1]), s.q_pids, s.g_pids[g0:g1], s.q_camids, s.g_camids[g0:g1],
+                                k=k, g_offset=g0)
+        idx_parts.append(i)
+        val_parts.append(v)
+    idx_all, val_all = torch.stack(idx_parts).contiguous(), torch.stack(val_parts).contiguous()
+    idx = torch.empty_like(idx_parts[0])
+    val = torch.empty_like(val_parts[0])
+    _lib.call("ieee_topk_merge", idx_all.data_ptr(), val_all.data_ptr(), shards, d.shape[0], k, idx.data_ptr(), val.data_ptr(),
+              _lib.stream())
+    assert np.array_equal(idx.cpu().numpy(), idx_o) and np.array_equal(val.cpu().numpy(), val_o)
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    s = make_retrieval_set(500, 3001, 40, 4, dim=256, sigma=2.5, seed=17, distractor_frac=0.1)
+    g0, g1 = shard_bounds(3001, world, rank)
+    ev = RetrievalEvaluator(s.gf[g0:g1].cuda(), s.g_pids[g0:g1], s.g_camids[g0:g1], group=dist.group.WORLD, g_offset=g0,
+                            g_total=3001)
+    cmc, mAP, info = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True)
+    gathered = [torch.empty((500, shard_bounds(3001, world, r)[1] - shard_bounds(3001, world, r)[0]), device="cuda") for r in range(world)]
+    dist.all_gather(gathered, info["distmat"].contiguous())
+    if rank == 0:
+        out["cmc"], out["mAP"], out["d"] = cmc, mAP, torch.cat(gathered, 1).cpu().numpy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_nccl_evaluation():
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    s = make_retrieval_set(500, 3001, 40, 4, dim=256, sigma=2.5, seed=17, distractor_frac=0.1)
+    cmc_o, map_o = R.evaluate_rank(out["d"], s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert np.array_equal(out["cmc"], cmc_o) and abs(out["mAP"] - map_o) < 1e-9
