@@ -43,15 +43,14 @@ def load_peaks():
 
 
 def make_workload(n_gpus: int):
-    from ieee_b200.testing import make_retrieval_set
-    return make_retrieval_set(Q_BASE * n_gpus, G_TOTAL, PIDS, CAMS, dim=DIM, sigma=3.5, seed=1, distractor_frac=0.17,
-                              name="market1501_shaped")
+    from ieee_b200.testing import market1501_shaped
+    return market1501_shaped(seed=1, num_q=Q_BASE * n_gpus)
 
 
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None

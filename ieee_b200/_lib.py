@@ -38,6 +38,7 @@ SIGNATURES = {
     "ieee_distmat": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, i64, vp, sz, vp]),
     "ieee_gallery_group_bytes": (sz, [i64]),
     "ieee_gallery_group": (C.c_int, [vp, i64, vp, vp]),
+    "ieee_rank_list_cap": (C.c_int, [vp, i64, vp, i64, vp, vp]),
     "ieee_rank_list_cap_sync": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(i32), vp]),
     "ieee_rank_gather": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "ieee_rank_count_smem_bytes": (sz, [i32, i32]),

@@ -191,6 +191,13 @@ int ieee_gallery_group(const int64_t* g_pids, int64_t G, void* group, ieee_strea
   return gallery_group(g_pids, G, group, (cudaStream_t)stream);
 }
 
+int ieee_rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* cap_dev, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(group && q_pids && cap_dev, "rank_list_cap: null pointer");
+  return rank_list_cap(group, G, q_pids, Q, cap_dev, (cudaStream_t)stream);
+}
+
 int ieee_rank_list_cap_sync(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* scratch_dev,
                             int32_t* cap_host, ieee_stream_t stream) {
   int rc = check_device();

@@ -39,134 +39,110 @@ __host__ __device__ __forceinline__ int next_pow2(int x) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Gallery grouping: sort (pid, local index) ascending.  Bitonic: chunks of kSortChunk in shared memory, wider
-// compare-exchange distances in global memory.  Once per gallery (shard), reused by every query block.
+// Gallery grouping: an open-addressing hash table pid -> (offset, count) into `members`, the gallery indices
+// grouped by identity.  Four small kernels (insert+count, allocate, fill) instead of a sort; once per gallery
+// (shard), reused by every query block.  Order inside a group is arbitrary -- the consumers sort what they take.
 // ---------------------------------------------------------------------------------------------------------
+static constexpr long long kEmptyPid = (long long)0x8080808080808080ull;   // memset(0x80) pattern; not a usable pid
+
 struct GroupView {
-  int64_t* pids;   // [Gp]
-  int32_t* idx;    // [Gp]
-  int64_t Gp;
+  long long* keys;     // [T]  pid of the slot or kEmptyPid
+  int32_t* cnt;        // [T]  members of that pid
+  int32_t* fill;       // [T]  fill cursor (== cnt when built)
+  int32_t* cursor;     // [1]  allocation cursor (+ padding)
+  int32_t* off;        // [T]  first member
+  int32_t* slot_of;    // [G]
+  int32_t* members;    // [G]  gallery indices grouped by pid
+  int64_t T;
+  size_t zero_off, zero_bytes, total;
 };
-static inline int64_t group_padded(int64_t G) {
-  int64_t p = 1;
-  while (p < G) p <<= 1;
-  return p < 2 ? 2 : p;
-}
 static inline GroupView group_view(const void* blob, int64_t G) {
   GroupView v;
-  v.Gp = group_padded(G);
+  int64_t T = 16;
+  while (T < 2 * G) T <<= 1;
+  v.T = T;
   uint8_t* b = static_cast<uint8_t*>(const_cast<void*>(blob));
-  v.pids = reinterpret_cast<int64_t*>(b);
-  v.idx = reinterpret_cast<int32_t*>(b + align256(size_t(v.Gp) * 8));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
+  v.keys = reinterpret_cast<long long*>(b + take(size_t(T) * 8));
+  v.zero_off = o;
+  v.cnt = reinterpret_cast<int32_t*>(b + take(size_t(T) * 4));
+  v.fill = reinterpret_cast<int32_t*>(b + take(size_t(T) * 4));
+  v.cursor = reinterpret_cast<int32_t*>(b + take(256));
+  v.zero_bytes = o - v.zero_off;
+  v.off = reinterpret_cast<int32_t*>(b + take(size_t(T) * 4));
+  v.slot_of = reinterpret_cast<int32_t*>(b + take(size_t(G) * 4));
+  v.members = reinterpret_cast<int32_t*>(b + take(size_t(G) * 4));
+  v.total = o;
   return v;
 }
-size_t gallery_group_bytes(int64_t G) {
-  const int64_t Gp = group_padded(G);
-  return align256(size_t(Gp) * 8) + align256(size_t(Gp) * 4);
+size_t gallery_group_bytes(int64_t G) { return group_view(nullptr, G).total; }
+
+__device__ __forceinline__ uint32_t hash_pid(long long pid) {
+  uint64_t x = (uint64_t)pid;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;   // murmur3 finaliser
+  return (uint32_t)x;
+}
+// slot of `pid`, or -1 if the gallery has no such identity
+__device__ __forceinline__ int group_find(const long long* __restrict__ keys, int64_t T, long long pid) {
+  uint32_t h = hash_pid(pid) & (uint32_t)(T - 1);
+  while (true) {
+    const long long k = keys[h];
+    if (k == pid) return (int)h;
+    if (k == kEmptyPid) return -1;
+    h = (h + 1) & (uint32_t)(T - 1);
+  }
 }
 
-constexpr int kSortChunk = 8192;   // (pid, idx) pairs sorted per CTA in shared memory: 96 KB
-
-__device__ __forceinline__ bool pair_greater(int64_t pa, int32_t ia, int64_t pb, int32_t ib) {
-  return pa > pb || (pa == pb && ia > ib);
+__global__ void group_insert_kernel(const int64_t* __restrict__ g_pids, int64_t G, long long* keys, int32_t* cnt,
+                                    int32_t* slot_of, int64_t T) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const long long pid = g_pids[g];
+  uint32_t h = hash_pid(pid) & (uint32_t)(T - 1);
+  while (true) {
+    const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(keys + h), (unsigned long long)kEmptyPid,
+                                                (unsigned long long)pid);
+    if (prev == kEmptyPid || prev == pid) break;
+    h = (h + 1) & (uint32_t)(T - 1);
+  }
+  atomicAdd(cnt + h, 1);
+  slot_of[g] = (int32_t)h;
 }
-
-// k_start == 2 : load the raw ids (fused initialisation: entry i = (g_pids[i], i), padding sorts last) and fully
-//                sort each chunk (all k <= chunk).
-// k_start  > 2 : the j < chunk tail of merge step k = k_start on already initialised arrays.
-__global__ void __launch_bounds__(1024) group_sort_local_kernel(const int64_t* __restrict__ g_pids, int64_t G, int64_t* pids,
-                                                                 int32_t* idx, int64_t Gp, int64_t k_start) {
-  extern __shared__ __align__(16) uint8_t gs_raw[];
-  int64_t* sp = reinterpret_cast<int64_t*>(gs_raw);
-  int32_t* si = reinterpret_cast<int32_t*>(sp + kSortChunk);
-  const int64_t base = (int64_t)blockIdx.x * kSortChunk;
-  const int n = (int)min((int64_t)kSortChunk, Gp - base);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t gi = base + i;
-    if (k_start == 2) {
-      sp[i] = gi < G ? g_pids[gi] : INT64_MAX;
-      si[i] = gi < G ? (int32_t)gi : INT32_MAX;
-    } else {
-      sp[i] = pids[gi];
-      si[i] = idx[gi];
-    }
-  }
-  const int64_t k_end = (k_start == 2) ? n : k_start;
-  for (int64_t k = k_start; k <= k_end; k <<= 1) {
-    int j0 = (int)min(k >> 1, (int64_t)(n >> 1));
-    for (int j = j0; j > 0; j >>= 1) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int p = i ^ j;
-        if (p > i) {
-          const bool up = ((base + i) & k) == 0;
-          if (pair_greater(sp[i], si[i], sp[p], si[p]) == up) {
-            int64_t tp = sp[i]; sp[i] = sp[p]; sp[p] = tp;
-            int32_t ti = si[i]; si[i] = si[p]; si[p] = ti;
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { pids[base + i] = sp[i]; idx[base + i] = si[i]; }
+__global__ void group_alloc_kernel(const int32_t* __restrict__ cnt, int32_t* off, int32_t* cursor, int64_t T) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < T && cnt[s] > 0) off[s] = atomicAdd(cursor, cnt[s]);
 }
-
-__global__ void group_sort_global_kernel(int64_t* pids, int32_t* idx, int64_t Gp, int64_t j, int64_t k) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Gp) return;
-  const int64_t p = i ^ j;
-  if (p > i) {
-    const bool up = (i & k) == 0;
-    const int64_t pa = pids[i], pb = pids[p];
-    const int32_t ia = idx[i], ib = idx[p];
-    if (pair_greater(pa, ia, pb, ib) == up) { pids[i] = pb; pids[p] = pa; idx[i] = ib; idx[p] = ia; }
-  }
+__global__ void group_fill_kernel(const int32_t* __restrict__ slot_of, const int32_t* __restrict__ off, int32_t* fill,
+                                  int32_t* members, int64_t G) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int s = slot_of[g];
+  members[off[s] + atomicAdd(fill + s, 1)] = (int32_t)g;
 }
 
 int gallery_group(const int64_t* g_pids, int64_t G, void* blob, cudaStream_t stream) {
-  IEEE_REQUIRE(g_pids && blob && G > 0 && G < (int64_t(1) << 31), "gallery_group: bad arguments (G=%lld)", (long long)G);
+  IEEE_REQUIRE(g_pids && blob && G > 0 && G < (int64_t(1) << 30), "gallery_group: bad arguments (G=%lld)", (long long)G);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 255) == 0, "gallery_group: blob must be 256-byte aligned");
   GroupView v = group_view(blob, G);
-  const int threads = 256;
-  const size_t smem = size_t(kSortChunk) * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(group_sort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const unsigned chunks = (unsigned)((v.Gp + kSortChunk - 1) / kSortChunk);
-  group_sort_local_kernel<<<chunks, 1024, smem, stream>>>(g_pids, G, v.pids, v.idx, v.Gp, 2);
-  count_launch();
-  for (int64_t k = 2 * (int64_t)kSortChunk; k <= v.Gp; k <<= 1) {
-    for (int64_t j = k >> 1; j >= kSortChunk; j >>= 1) {
-      group_sort_global_kernel<<<(unsigned)((v.Gp + threads - 1) / threads), threads, 0, stream>>>(v.pids, v.idx, v.Gp, j, k);
-      count_launch();
-    }
-    group_sort_local_kernel<<<chunks, 1024, smem, stream>>>(g_pids, G, v.pids, v.idx, v.Gp, k);
-    count_launch();
-  }
+  IEEE_CUDA_CHECK(cudaMemsetAsync(v.keys, 0x80, size_t(v.T) * 8, stream));
+  IEEE_CUDA_CHECK(cudaMemsetAsync(static_cast<uint8_t*>(blob) + v.zero_off, 0, v.zero_bytes, stream));
+  const int th = 256;
+  group_insert_kernel<<<(unsigned)((G + th - 1) / th), th, 0, stream>>>(g_pids, G, v.keys, v.cnt, v.slot_of, v.T);
+  group_alloc_kernel<<<(unsigned)((v.T + th - 1) / th), th, 0, stream>>>(v.cnt, v.off, v.cursor, v.T);
+  group_fill_kernel<<<(unsigned)((G + th - 1) / th), th, 0, stream>>>(v.slot_of, v.off, v.fill, v.members, G);
+  count_launch(3);
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
 
-// [lo, hi) of `pid` in the sorted id array.
-__device__ __forceinline__ void pid_range(const int64_t* __restrict__ sp, int64_t n, int64_t pid, int64_t& lo, int64_t& hi) {
-  int64_t a = 0, b = n;
-  while (a < b) { int64_t m = (a + b) >> 1; if (sp[m] < pid) a = m + 1; else b = m; }
-  lo = a;
-  b = n;
-  while (a < b) { int64_t m = (a + b) >> 1; if (sp[m] <= pid) a = m + 1; else b = m; }
-  hi = a;
-}
-
-__global__ void list_cap_kernel(const int64_t* __restrict__ sp, int64_t Gp, const int64_t* __restrict__ q_pids, int64_t Q,
-                                int32_t* cap_out) {
+__global__ void list_cap_kernel(const long long* __restrict__ keys, const int32_t* __restrict__ cnt, int64_t T,
+                                const int64_t* __restrict__ q_pids, int64_t Q, int32_t* cap_out) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int32_t n = 0;
   if (q < Q) {
-    int64_t lo, hi;
-    pid_range(sp, Gp, q_pids[q], lo, hi);
-    n = (int32_t)(hi - lo);
+    const int s = group_find(keys, T, q_pids[q]);
+    n = s >= 0 ? cnt[s] : 0;
   }
   for (int o = 16; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
   if ((threadIdx.x & 31) == 0 && n > 0) atomicMax(cap_out, n);
@@ -176,7 +152,7 @@ int rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q
   GroupView v = group_view(group, G);
   IEEE_CUDA_CHECK(cudaMemsetAsync(cap_dev, 0, 4, stream));
   if (Q > 0) {
-    list_cap_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(v.pids, v.Gp, q_pids, Q, cap_dev);
+    list_cap_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(v.keys, v.cnt, v.T, q_pids, Q, cap_dev);
     count_launch();
   }
   IEEE_CUDA_CHECK(cudaGetLastError());
@@ -188,31 +164,33 @@ int rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
                                                            const int64_t* __restrict__ q_pids, const int64_t* __restrict__ q_camids,
-                                                           const int64_t* __restrict__ g_camids, const int64_t* __restrict__ sp,
-                                                           const int32_t* __restrict__ sidx, int64_t Gp, int64_t g_offset,
+                                                           const int64_t* __restrict__ g_camids, const long long* __restrict__ keys,
+                                                           const int32_t* __restrict__ gcnt, const int32_t* __restrict__ goff,
+                                                           const int32_t* __restrict__ members, int64_t T, int64_t g_offset,
                                                            int32_t cap, uint64_t* __restrict__ rel, int32_t* __restrict__ n_rel,
                                                            uint64_t* __restrict__ junk, int32_t* __restrict__ n_junk,
                                                            int32_t* __restrict__ overflow) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
-  const int64_t pid = q_pids[q], cam = q_camids[q];
-  int64_t lo = 0, hi = 0;
-  if (lane == 0) pid_range(sp, Gp, pid, lo, hi);
+  const int64_t cam = q_camids[q];
+  int lo = 0, n = 0;
+  if (lane == 0) {
+    const int s = group_find(keys, T, q_pids[q]);
+    if (s >= 0) { lo = goff[s]; n = gcnt[s]; }
+  }
   lo = __shfl_sync(0xffffffffu, lo, 0);
-  hi = __shfl_sync(0xffffffffu, hi, 0);
+  n = __shfl_sync(0xffffffffu, n, 0);
   int nr = 0, nj = 0;
-  for (int64_t t0 = lo; t0 < hi; t0 += 32) {
-    const int64_t t = t0 + lane;
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int t = t0 + lane;
     bool is_rel = false, is_junk = false;
     uint64_t key = 0;
-    if (t < hi) {
-      const int32_t gi = sidx[t];
-      if (gi >= 0 && gi < G) {   // padding entries carry INT32_MAX
-        key = pack_key(distmat[q * ld + gi], (uint32_t)(gi + g_offset));
-        is_junk = g_camids[gi] == cam;
-        is_rel = !is_junk;
-      }
+    if (t < n) {
+      const int32_t gi = members[lo + t];
+      key = pack_key(distmat[q * ld + gi], (uint32_t)(gi + g_offset));
+      is_junk = g_camids[gi] == cam;
+      is_rel = !is_junk;
     }
     const unsigned mr = __ballot_sync(0xffffffffu, is_rel), mj = __ballot_sync(0xffffffffu, is_junk);
     const unsigned below = (1u << lane) - 1;
@@ -234,73 +212,178 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
 // Every distance is binned against the query's sorted thresholds T_0 < ... < T_{R-1} (the relevant items' packed
 // (distance key, global index)): b(e) = #{k : T_k <lex e}.  A 1024-cell table over [d(T_0), d(T_{R-1})] maps a
 // distance to its bin with one multiply and one shared-memory load; only cells that contain a threshold need
-// exact 64-bit compares.  Bin counters are PRIVATE per thread (16-bit, layout [bin][thread]: conflict-free plain
-// read-modify-write, no atomics) and are summed once after the stream; queries with more relevant items than
-// the private table can hold fall back to shared atomics.
+// exact 64-bit compares.  Bin counters are PRIVATE per thread (32-bit, layout [bin][thread]: conflict-free plain
+// read-modify-write, no atomics) and are summed once after the stream; queries whose R + 2 bins do not fit the
+// private table, or whose thresholds are not finite, fall back to shared atomics / binary search.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kCountThreads = 256;
 constexpr int kLutCells = 1024;
-constexpr int kPrivateBinBudget = 96 * 1024;   // bytes of private counters per CTA ((R + 2) * 512 B)
+constexpr int kPrivateBinBudget = 64 * 1024;   // bytes of private counters per CTA ((R + 2) * 1 KB)
 
-__host__ __device__ inline size_t count_smem_bytes(int Rp, bool priv) {
-  // T[Rp] u64 | hist[Rp + 2] i32 | cell[L] u32 | misc[64] i32 | priv[(Rp + 2) * threads] u16
-  return size_t(Rp) * 8 + size_t(Rp + 2 + kLutCells + 64) * 4 + (priv ? size_t(Rp + 2) * kCountThreads * 2 : 0);
+struct CountSmemPlan { size_t hist_off, cell_off, misc_off, priv_off, total; int priv_bins; };
+__host__ __device__ inline CountSmemPlan count_smem_plan(int Rp) {
+  CountSmemPlan p;
+  p.hist_off = size_t(Rp) * 8;                          // after T[Rp] u64
+  p.cell_off = p.hist_off + size_t(Rp + 2) * 4;         // hist[Rp + 2] i32
+  p.misc_off = p.cell_off + size_t(kLutCells) * 4;      // cell[L] u32
+  p.priv_off = (p.misc_off + 64 * 4 + 15) & ~size_t(15);
+  const int want = Rp + 2;
+  p.priv_bins = want * kCountThreads * 4 <= kPrivateBinBudget ? want : kPrivateBinBudget / (kCountThreads * 4);
+  p.total = p.priv_off + size_t(p.priv_bins) * kCountThreads * 4;
+  return p;
 }
 
-// b(e) = lo + #{k in [lo, lo+n) : T_k <lex e}; `same` = #{k : key(T_k) == key(e)}; is_thr = e is itself a threshold
-__device__ __forceinline__ int exact_bin(const uint64_t* T, int lo, int n, uint64_t pe, int& same, bool& is_thr) {
-  int b = lo;
+enum CountMode { COUNT_LUT_PRIVATE = 0, COUNT_LUT_ATOMIC = 1, COUNT_SEARCH_ATOMIC = 2 };
+
+struct CountCtx {
+  const uint64_t* T;
+  const uint32_t* cell;
+  int32_t* hist;
+  int32_t* priv;        // this thread's column: priv[b * kCountThreads]
+  float lo, hi, scale;
+  uint32_t kmax;
+  int R, trash;
+  uint32_t g_offset;
+  int ties;
+};
+
+// b(e) = lo + #{k in [lo, lo+n) : T_k <lex e}; ties += #{k : key(T_k) == key(e)} unless e is itself a threshold
+__device__ __forceinline__ int exact_bin(CountCtx& c, int lo, int n, uint64_t pe) {
+  int b = lo, same = 0;
+  bool is_thr = false;
   const uint32_t ke = (uint32_t)(pe >> 32);
   for (int j = lo; j < lo + n; ++j) {
-    const uint64_t t = T[j];
+    const uint64_t t = c.T[j];
     b += (t < pe);
     same += ((uint32_t)(t >> 32) == ke);
     is_thr |= (t == pe);
   }
+  if (!is_thr) c.ties += same;
   return b;
 }
 
-template <bool kPrivate>
+// Branch-free per-element body (the lanes of a warp must stay converged over the 16 elements in flight): every
+// element increments exactly one counter -- bin 0 if it precedes all thresholds, the trash bin R + 1 if it follows
+// them (or is NaN), else its bin from the cell table; only cells that hold a threshold take a (reconverging) branch.
+template <int MODE>
+__device__ __forceinline__ void count_visit(CountCtx& c, float d, uint32_t g) {
+  int b;
+  if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
+    // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
+    const bool in = d <= c.hi;
+    const bool before = d < c.lo;
+    const uint32_t ce = c.cell[(int)((d - c.lo) * c.scale) & (kLutCells - 1)];   // garbage-safe: masked, then overridden
+    b = (int)(ce & 0xFFFFFu);
+    if (in && !before && (ce >> 20)) b = exact_bin(c, b, (int)(ce >> 20), pack_key(d, g + c.g_offset));
+    b = before ? 0 : b;
+    b = in ? b : c.trash;
+  } else {
+    const uint32_t ke = order_key(d);
+    const uint64_t pe = (uint64_t(ke) << 32) | (g + c.g_offset);
+    int a = 0, e = c.R;
+    while (a < e) { const int m = (a + e) >> 1; if (c.T[m] < pe) a = m + 1; else e = m; }
+    int same = 0;
+    bool is_thr = false;
+    for (int j = a; j < c.R && (uint32_t)(c.T[j] >> 32) == ke; ++j) { same++; is_thr |= (c.T[j] == pe); }
+    for (int j = a - 1; j >= 0 && (uint32_t)(c.T[j] >> 32) == ke; --j) same++;
+    if (!is_thr) c.ties += same;
+    b = (ke > c.kmax) ? c.trash : a;
+  }
+  if constexpr (MODE == COUNT_LUT_PRIVATE) c.priv[b * kCountThreads] += 1;
+  else atomicAdd(&c.hist[b], 1);
+}
+
+template <int MODE>
+__device__ __forceinline__ void count_stream(CountCtx& c, const float* __restrict__ row, int G) {
+  const int tid = threadIdx.x;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
+  int head = (int)(((16 - (addr & 15)) & 15) >> 2);
+  if (head > G) head = G;
+  for (int g = tid; g < head; g += kCountThreads) count_visit<MODE>(c, row[g], (uint32_t)g);
+  const int nvec = (G - head) >> 2;
+  const float4* rv = reinterpret_cast<const float4*>(row + head);
+  int i = tid;
+  if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
+    for (; i + 3 * kCountThreads < nvec; i += 4 * kCountThreads) {   // 4 independent 16-byte loads in flight
+      const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + kCountThreads), a2 = __ldcs(rv + i + 2 * kCountThreads),
+                   a3 = __ldcs(rv + i + 3 * kCountThreads);
+      uint32_t g0 = (uint32_t)(head + 4 * i);
+      count_visit<MODE>(c, a0.x, g0); count_visit<MODE>(c, a0.y, g0 + 1); count_visit<MODE>(c, a0.z, g0 + 2); count_visit<MODE>(c, a0.w, g0 + 3);
+      g0 += 4 * kCountThreads;
+      count_visit<MODE>(c, a1.x, g0); count_visit<MODE>(c, a1.y, g0 + 1); count_visit<MODE>(c, a1.z, g0 + 2); count_visit<MODE>(c, a1.w, g0 + 3);
+      g0 += 4 * kCountThreads;
+      count_visit<MODE>(c, a2.x, g0); count_visit<MODE>(c, a2.y, g0 + 1); count_visit<MODE>(c, a2.z, g0 + 2); count_visit<MODE>(c, a2.w, g0 + 3);
+      g0 += 4 * kCountThreads;
+      count_visit<MODE>(c, a3.x, g0); count_visit<MODE>(c, a3.y, g0 + 1); count_visit<MODE>(c, a3.z, g0 + 2); count_visit<MODE>(c, a3.w, g0 + 3);
+    }
+  }
+  for (; i < nvec; i += kCountThreads) {
+    const float4 a = __ldcs(rv + i);
+    const uint32_t g0 = (uint32_t)(head + 4 * i);
+    count_visit<MODE>(c, a.x, g0); count_visit<MODE>(c, a.y, g0 + 1); count_visit<MODE>(c, a.z, g0 + 2); count_visit<MODE>(c, a.w, g0 + 3);
+  }
+  for (int g = head + 4 * nvec + tid; g < G; g += kCountThreads) count_visit<MODE>(c, row[g], (uint32_t)g);
+}
+
 __global__ void __launch_bounds__(kCountThreads)
-rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
+rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
                   int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
                   const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                   unsigned long long* __restrict__ ties_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
+  const CountSmemPlan plan = count_smem_plan(Rp);
   uint64_t* T = reinterpret_cast<uint64_t*>(cs_raw);
-  int32_t* hist = reinterpret_cast<int32_t*>(cs_raw + size_t(Rp) * 8);
-  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + Rp + 2);     // first bin of the cell | (#thresholds in it) << 20
-  int32_t* misc = reinterpret_cast<int32_t*>(cell + kLutCells);    // [0] R, [1] ties (signed), [2..] scan scratch
-  uint16_t* priv = reinterpret_cast<uint16_t*>(misc + 64);         // [(R + 1)][kCountThreads]
+  int32_t* hist = reinterpret_cast<int32_t*>(cs_raw + plan.hist_off);
+  uint32_t* cell = reinterpret_cast<uint32_t*>(cs_raw + plan.cell_off);   // first bin of the cell | (#thresholds in it) << 20
+  int32_t* misc = reinterpret_cast<int32_t*>(cs_raw + plan.misc_off);    // [0] R, [1] ties (signed), [2..] scan scratch
+  int32_t* priv = reinterpret_cast<int32_t*>(cs_raw + plan.priv_off);    // [bins][kCountThreads]
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   const int stride = shards * cap + 1;
   int32_t* out = counts + q * stride;
 
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
-  for (int i = tid; i < Rp; i += kCountThreads) T[i] = kPadKey;
-  for (int i = tid; i < Rp + 2; i += kCountThreads) hist[i] = 0;
-  for (int i = tid; i < kLutCells; i += kCountThreads) cell[i] = 0;
   if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+  for (int i = tid; i < kLutCells; i += kCountThreads) cell[i] = 0;
   __syncthreads();
+  // unsorted staging: the (not yet live) private-bin area when it is large enough, else T itself
+  const bool stage_in_priv = size_t(Rp) * 8 <= size_t(plan.priv_bins) * kCountThreads * 4;
+  uint64_t* Tin = stage_in_priv ? reinterpret_cast<uint64_t*>(priv) : T;
   for (int s = 0; s < shards; ++s) {
     const int n = n_rel_all[(int64_t)s * Q + q];
     const uint64_t* src = rel_all + ((int64_t)s * Q + q) * cap;
     __shared__ int base_s;
     if (tid == 0) { base_s = misc[0]; misc[0] += n; }
     __syncthreads();
-    for (int i = tid; i < n; i += kCountThreads) T[base_s + i] = src[i];
+    for (int i = tid; i < n; i += kCountThreads) Tin[base_s + i] = src[i];
     __syncthreads();
   }
   const int R = misc[0];
   const int nj = n_junk[q];
   if (tid == 0) out[stride - 1] = nj;
   if (R == 0) return;   // invalid query (rank.py:142-144): nothing to rank against
-  block_bitonic_sort(T, next_pow2(max(R, 2)));
-  if constexpr (kPrivate) {
-    uint32_t* pz = reinterpret_cast<uint32_t*>(priv);
-    for (int i = tid; i < (R + 2) * kCountThreads / 2; i += kCountThreads) pz[i] = 0;
+  if (stage_in_priv && R <= 512) {
+    // rank sort: keys are distinct (distinct gallery indices), so #smaller is each key's final position
+    for (int k = tid; k < R; k += kCountThreads) {
+      const uint64_t me = Tin[k];
+      int pos = 0;
+      for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
+      T[pos] = me;
+    }
+  } else {
+    const int np = next_pow2(max(R, 2));
+    if (stage_in_priv) {
+      for (int i = tid; i < np; i += kCountThreads) T[i] = i < R ? Tin[i] : kPadKey;
+    } else {
+      for (int i = R + tid; i < np; i += kCountThreads) T[i] = kPadKey;
+    }
+    block_bitonic_sort(T, np);
   }
+  __syncthreads();
+  for (int i = tid; i < R + 2; i += kCountThreads) hist[i] = 0;
+  const bool priv_ok = R + 2 <= plan.priv_bins;
+  if (priv_ok)
+    for (int i = tid; i < (R + 2) * kCountThreads; i += kCountThreads) priv[i] = 0;
 
   // ---- cell table over [lo, hi] of the threshold distances ----------------------------------------------
   const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
@@ -308,124 +391,52 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   const float span = hi - lo;
   const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f &&
                        isfinite((float)kLutCells / span) && R < (1 << 11);
-  const float scale = use_lut ? (float)kLutCells / span : 0.f;
+  // (hi - lo) * scale = kLutCells - 0.5: every in-range distance lands in [0, kLutCells) without a clamp, and the map
+  // stays monotone (the -0.5 margin dwarfs fp32 rounding); out-of-range / NaN elements are only masked into range
+  const float scale = use_lut ? ((float)kLutCells - 0.5f) / span : 0.f;
   if (use_lut) {
     for (int k = tid; k < R; k += kCountThreads) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
-      const int c = min((int)((d - lo) * scale), kLutCells - 1);
-      atomicAdd(&cell[c], 1u << 20);
+      atomicAdd(&cell[(int)((d - lo) * scale) & (kLutCells - 1)], 1u << 20);
     }
     __syncthreads();
     // exclusive scan of the per-cell counts -> first bin of each cell (kLutCells == 4 * kCountThreads)
-    {
-      int v[4], sum = 0;
+    int v[4], sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[j] = (int)(cell[tid * 4 + j] >> 20); sum += v[j]; }
-      int incl = sum;
-      const int lane = tid & 31, w = tid >> 5;
+    for (int j = 0; j < 4; ++j) { v[j] = (int)(cell[tid * 4 + j] >> 20); sum += v[j]; }
+    int incl = sum;
+    const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-      int32_t* wsum = misc + 2;
-      if (lane == 31) wsum[w] = incl;
-      __syncthreads();
-      int woff = 0;
-      for (int i = 0; i < w; ++i) woff += wsum[i];
-      int run = woff + incl - sum;
+    for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    int32_t* wsum = misc + 2;
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < w; ++i) woff += wsum[i];
+    int run = woff + incl - sum;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { cell[tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
-    }
+    for (int j = 0; j < 4; ++j) { cell[tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
   }
   __syncthreads();
-
   // ---- stream the row ---------------------------------------------------------------------------------------
+  CountCtx c;
+  c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + tid;
+  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1;
+  c.g_offset = (uint32_t)g_offset; c.ties = 0;
   const float* row = distmat + q * ld;
-  int tie_local = 0;
-  // 16-bit slot of this thread inside a bin's 256 counters: 32-bit word = lane + 32 * (warp & 3), half = warp >> 2,
-  // so the 32 lanes of a warp always touch 32 different banks whatever their bins are
-  const int priv_slot = (((tid & 31) + 32 * ((tid >> 5) & 3)) << 1) | (tid >> 7);
-  // Branch-free per-element body (lanes must stay converged across the 16 elements in flight): every element
-  // increments exactly one counter -- bin 0 if it precedes all thresholds, the trash bin R + 1 if it follows them
-  // (or is NaN), else its bin from the cell table; only cells that hold a threshold take a (reconverging) branch.
-  const int trash = R + 1;
-  const bool may_wrap = (G + kCountThreads - 1) / kCountThreads >= 0xFFFF;   // uniform; false below 16.7 M columns
-  auto bump = [&](int b) {
-    if constexpr (kPrivate) {
-      uint16_t* p16 = priv + b * kCountThreads + priv_slot;
-      const uint16_t nv = (uint16_t)(*p16 + 1);
-      *p16 = nv;
-      if (may_wrap && nv == 0xFFFFu) { atomicAdd(&hist[b], 0xFFFF); *p16 = 0; }   // spill before the counter can wrap
-    } else {
-      atomicAdd(&hist[b], 1);
-    }
-  };
-  auto visit = [&](float d, int64_t g) {
-    int b;
-    if (use_lut) {
-      // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
-      const bool in = d <= hi;
-      const bool before = d < lo;
-      const int ci = max(0, min((int)((d - lo) * scale), kLutCells - 1));
-      const uint32_t ce = cell[ci];
-      b = (int)(ce & 0xFFFFFu);
-      if (in && !before && (ce >> 20)) {           // the cell holds thresholds: exact (key, index) compares
-        const uint64_t pe = pack_key(d, (uint32_t)(g + g_offset));
-        int same = 0;
-        bool is_thr = false;
-        b = exact_bin(T, b, (int)(ce >> 20), pe, same, is_thr);
-        if (!is_thr) tie_local += same;
-      }
-      b = before ? 0 : b;
-      b = in ? b : trash;
-    } else {                                       // non-finite / degenerate thresholds: search all of T
-      const uint32_t ke = order_key(d);
-      const uint64_t pe = (uint64_t(ke) << 32) | (uint32_t)(g + g_offset);
-      int a = 0, e = R;
-      while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
-      int same = 0;
-      bool is_thr = false;
-      for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) { same++; is_thr |= (T[j] == pe); }
-      for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) same++;
-      if (!is_thr) tie_local += same;
-      b = (ke > kmax) ? trash : a;
-    }
-    bump(b);
-  };
-  {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
-    int64_t head = ((16 - (addr & 15)) & 15) >> 2;
-    if (head > G) head = G;
-    for (int64_t g = tid; g < head; g += kCountThreads) visit(row[g], g);
-    const int64_t nvec = (G - head) >> 2;
-    const float4* rv = reinterpret_cast<const float4*>(row + head);
-    int64_t i = tid;
-    for (; i + 3 * kCountThreads < nvec; i += 4 * kCountThreads) {   // 4 independent 16-byte loads in flight
-      float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + kCountThreads), a2 = __ldcs(rv + i + 2 * kCountThreads),
-             a3 = __ldcs(rv + i + 3 * kCountThreads);
-      int64_t g0 = head + 4 * i;
-      visit(a0.x, g0); visit(a0.y, g0 + 1); visit(a0.z, g0 + 2); visit(a0.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      visit(a1.x, g0); visit(a1.y, g0 + 1); visit(a1.z, g0 + 2); visit(a1.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      visit(a2.x, g0); visit(a2.y, g0 + 1); visit(a2.z, g0 + 2); visit(a2.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      visit(a3.x, g0); visit(a3.y, g0 + 1); visit(a3.z, g0 + 2); visit(a3.w, g0 + 3);
-    }
-    for (; i < nvec; i += kCountThreads) {
-      const float4 a = __ldcs(rv + i);
-      const int64_t g0 = head + 4 * i;
-      visit(a.x, g0); visit(a.y, g0 + 1); visit(a.z, g0 + 2); visit(a.w, g0 + 3);
-    }
-    for (int64_t g = head + 4 * nvec + tid; g < G; g += kCountThreads) visit(row[g], g);
-  }
+  if (!use_lut) count_stream<COUNT_SEARCH_ATOMIC>(c, row, G);
+  else if (priv_ok) count_stream<COUNT_LUT_PRIVATE>(c, row, G);
+  else count_stream<COUNT_LUT_ATOMIC>(c, row, G);
+  int tie_local = c.ties;
   __syncthreads();
-  if constexpr (kPrivate) {   // fold the private counters: warp w sums bins w, w + 8, ...
+  if (use_lut && priv_ok) {   // fold the private counters: warp w sums bins w, w + 8, ...
     const int lane = tid & 31, w = tid >> 5;
     for (int b = w; b <= R; b += kCountThreads / 32) {
       int sum = 0;
 #pragma unroll
       for (int j = 0; j < kCountThreads / 32; ++j) sum += priv[b * kCountThreads + j * 32 + lane];
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0 && sum) atomicAdd(&hist[b], sum);
+      if (lane == 0) hist[b] = sum;
     }
     __syncthreads();
   }
@@ -434,7 +445,6 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
     const uint64_t pe = junk[q * cap + i];
     const uint32_t ke = (uint32_t)(pe >> 32);
     if (ke > kmax) continue;
-    if (ke < kmin) { atomicSub(&hist[0], 1); continue; }
     int a = 0, e = R;
     while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
     for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) tie_local--;
@@ -471,37 +481,25 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int6
   if (tid == 0 && ties_out != nullptr && misc[1] != 0) atomicAdd(ties_out, (unsigned long long)(long long)misc[1]);
 }
 
-static inline bool count_use_private(int Rp) { return size_t(Rp + 2) * kCountThreads * 2 <= size_t(kPrivateBinBudget); }
-size_t rank_count_smem(int shards, int cap) {
-  const int Rp = next_pow2(max(shards * cap, 2));
-  return count_smem_bytes(Rp, count_use_private(Rp));
-}
+size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(max(shards * cap, 2))).total; }
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
                const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream) {
   IEEE_REQUIRE(distmat && rel_all && n_rel_all && junk && n_junk && counts, "rank_count: null pointer");
-  IEEE_REQUIRE(Q >= 0 && G > 0 && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
+  IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
   const int Rp = next_pow2(max(shards * cap, 2));
-  const bool priv = count_use_private(Rp);
-  const size_t smem = count_smem_bytes(Rp, priv);
+  const size_t smem = count_smem_plan(Rp).total;
   IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: shards*cap=%d relevant items per query exceed the shared-memory budget",
                shards * cap);
-  static size_t smem_set[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > smem_set[priv]) {
-    if (priv)
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[priv] = smem;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
   }
-  if (priv)
-    rank_count_kernel<true><<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, G, g_offset, shards, cap, Rp, rel_all,
-                                                                          n_rel_all, junk, n_junk, counts, ties);
-  else
-    rank_count_kernel<false><<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, G, g_offset, shards, cap, Rp, rel_all,
-                                                                           n_rel_all, junk, n_junk, counts, ties);
+  rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, Rp, rel_all,
+                                                                  n_rel_all, junk, n_junk, counts, ties);
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -516,8 +514,10 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
   IEEE_REQUIRE(g_offset >= 0 && g_offset + G <= (int64_t(1) << 32), "rank_gather: global gallery index must fit 32 bits");
   if (Q == 0) return IEEE_OK;
   GroupView v = group_view(group, G);
-  rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.pids, v.idx,
-                                                                  v.Gp, g_offset, cap, rel, n_rel, junk, n_junk, overflow); count_launch();
+  rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.keys, v.cnt,
+                                                                  v.off, v.members, v.T, g_offset, cap, rel, n_rel, junk, n_junk,
+                                                                  overflow);
+  count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }

@@ -81,6 +81,7 @@ class RetrievalEvaluator:
         self.G = self.gallery.rows
         self.g_total = self.G if g_total is None else g_total
         self._block = None
+        self._side = None
 
     # -- one query block ---------------------------------------------------------------------------------
     def _block_rows(self, Q: int) -> int:
@@ -113,12 +114,6 @@ class RetrievalEvaluator:
             Q = qf.shape[0]
             qp = _as_device(q_pids, torch.int64, self.device)
             qc = _as_device(q_camids, torch.int64, self.device)
-            cap = self.labels.list_cap(qp)
-            if self.world > 1:
-                import torch.distributed as dist_
-                cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
-                dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
-                cap = int(cap_t.item())
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
@@ -129,11 +124,29 @@ class RetrievalEvaluator:
                 # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
                 pitch = (self.G + 31) // 32 * 32
                 self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
+
+            def contraction(s, e):
+                qpk = PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
+                return packed_distmat(qpk, self.gallery, self._block[: e - s])
+
+            # list capacity: queried on a side stream; the first block's contraction is queued before the host
+            # waits for it, so the round trip costs no GPU time
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            cap_done, cap_host = self.labels.list_cap_async(qp, self._side)
+            dist = contraction(0, min(Q, rows))
+            cap_done.synchronize()
+            cap = max(int(cap_host.item()), 1)
+            if self.world > 1:
+                import torch.distributed as dist_
+                cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
+                dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
+                cap = int(cap_t.item())
             full = None
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)
-                qpk = PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
-                dist = packed_distmat(qpk, self.gallery, self._block[: e - s])
+                if s > 0:
+                    dist = contraction(s, e)
                 self._rank_block(dist, qp[s:e], qc[s:e], cap, ap[s:e], first[s:e], short[s:e], ties)
                 if return_distmat:
                     full = dist.clone() if full is None else torch.cat([full, dist], 0)

@@ -35,6 +35,21 @@ class GalleryLabels:
             _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
         self._scratch = torch.zeros(64, dtype=torch.int32, device=device)
 
+    def list_cap_async(self, q_pids: torch.Tensor, side: torch.cuda.Stream):
+        """Start the capacity query on `side` (after the work already queued on the current stream) and return an
+        event + pinned int32; the caller keeps queueing the contraction on its own stream and reads the value when
+        it needs it, so the host round trip hides behind the GEMM."""
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        if not hasattr(self, "_cap_host"):
+            self._cap_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        with torch.cuda.stream(side):
+            _lib.call("ieee_rank_list_cap", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
+                      self._scratch.data_ptr(), _lib.stream())
+            self._cap_host.copy_(self._scratch[:1], non_blocking=True)
+            done = side.record_event()
+        return done, self._cap_host
+
     def list_cap(self, q_pids: torch.Tensor) -> int:
         cap = C.c_int32(0)
         with torch.cuda.device(q_pids.device):

@@ -68,7 +68,7 @@ def rgbnt201_shaped(seed: int = 0, sigma: float = 3.5) -> RetrievalSet:
     return make_retrieval_set(836, 836, 30, 4, sigma=sigma, seed=seed, same_set=True, name="rgbnt201_shaped")
 
 
-def market1501_shaped(seed: int = 1, sigma: float = 3.5) -> RetrievalSet:
+def market1501_shaped(seed: int = 1, sigma: float = 2.75, num_q: int = 3368) -> RetrievalSet:
     """Config C2: 3368 queries x 15913 gallery (torchreid/data/datasets/image/market1501.py:21), 751 ids, 6 cameras."""
-    return make_retrieval_set(3368, 15913, 751, 6, sigma=sigma, seed=seed, distractor_frac=0.17,
+    return make_retrieval_set(num_q, 15913, 751, 6, sigma=sigma, seed=seed, distractor_frac=0.17,
                               name="market1501_shaped")

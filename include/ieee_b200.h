@@ -121,14 +121,17 @@ typedef struct {
   int64_t reserved[2];
 } ieee_eval_summary;
 
-/* Sort the (local) gallery's ids once: the group blob holds (pid, local index) pairs in ascending pid order
- * (padded to a power of two), so a query finds all gallery items of its identity by binary search instead of
- * scanning G labels.  g_pids: int64[G], G < 2^31. */
+/* Group the (local) gallery by identity once: the blob holds an open-addressing hash table pid -> (offset, count)
+ * into the gallery indices grouped by pid, so a query finds all gallery items of its identity with one probe
+ * instead of scanning G labels.  g_pids: int64[G], G < 2^30; the value 0x8080808080808080 is reserved. */
 size_t ieee_gallery_group_bytes(int64_t G);
-int ieee_gallery_group(const int64_t* g_pids, int64_t G, void* group /* ieee_gallery_group_bytes(G) */,
+int ieee_gallery_group(const int64_t* g_pids, int64_t G, void* group /* ieee_gallery_group_bytes(G), 256-aligned */,
                        ieee_stream_t stream);
 /* Largest number of (local) gallery items sharing an identity with any of the Q queries = the list capacity
- * `cap` the gather/count stages need.  scratch_dev: 4 bytes of device memory.  Synchronises the stream. */
+ * `cap` the gather/count stages need.  cap_dev: one int32 of device memory (written asynchronously);
+ * the _sync form also copies it to the host and synchronises the stream. */
+int ieee_rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* cap_dev,
+                       ieee_stream_t stream);
 int ieee_rank_list_cap_sync(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* scratch_dev,
                             int32_t* cap_host, ieee_stream_t stream);
 

@@ -42,7 +42,7 @@ def test_size_queries_need_no_gpu():
     # hi + lo planes of [rows, roundup(D,64)] 16-bit plus two fp32 per row (norm, scale), 256-byte aligned sections
     assert lib.ieee_packed_bytes(128, 2304, _lib.PRECISIONS["f16x3"]) == 2 * 128 * 2304 * 2 + 1024
     assert lib.ieee_packed_bytes(128, 100, _lib.PRECISIONS["bf16"]) == 128 * 128 * 2 + 1024
-    assert lib.ieee_gallery_group_bytes(15913) == 16384 * 12
+    assert lib.ieee_gallery_group_bytes(15913) >= 32768 * 20 + 15913 * 8     # hash table of 2^15 slots + member lists
     assert lib.ieee_rank_finalize_workspace_bytes(1000) > 0
 
 
