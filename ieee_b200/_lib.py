@@ -31,6 +31,7 @@ SIGNATURES = {
     "ieee_set_cta_group": (C.c_int, [C.c_int]),
     "ieee_launch_count": (i64, []),
     "ieee_set_debug_flags": (C.c_int, [C.c_int]),
+    "ieee_set_accum_chunk": (C.c_int, [C.c_int]),
     "ieee_packed_bytes": (sz, [i64, i64, C.c_int]),
     "ieee_pack_features": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
     "ieee_distmat_packed": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp]),

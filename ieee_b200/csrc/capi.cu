@@ -17,6 +17,7 @@ const char* get_error() { return g_error; }
 
 static std::atomic<long long> g_launches{0};
 int g_debug_flags = 0;
+int g_accum_chunk_kb = 4;
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
@@ -119,6 +120,12 @@ int ieee_device_info(int* sm, int* cc) {
 }
 
 int64_t ieee_launch_count(void) { return g_launches.load(); }
+
+int ieee_set_accum_chunk(int k_slices) {
+  const int prev = g_accum_chunk_kb;
+  if (k_slices >= 0) g_accum_chunk_kb = k_slices;
+  return prev;
+}
 
 int ieee_set_debug_flags(int flags) {
   const int prev = g_debug_flags;

@@ -38,7 +38,8 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
 void count_launch(int n = 1);
-extern int g_debug_flags;       // ieee_set_debug_flags()   // bookkeeping behind ieee_launch_count()
+extern int g_debug_flags;       // ieee_set_debug_flags()
+extern int g_accum_chunk_kb;    // ieee_set_accum_chunk(): K-slices per tensor-core accumulation chunk (0 = whole K)   // bookkeeping behind ieee_launch_count()
 
 // ---- total order on float distances -----------------------------------------------------------------
 // Ascending uint32 key == NumPy's ascending sort order: -0.0 == +0.0, every NaN equal and last.

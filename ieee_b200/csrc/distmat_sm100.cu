@@ -276,6 +276,232 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
 }
 
+// =====================================================================================================
+// Chunked-accumulation variant (cta_group::1).
+//
+// The tcgen05 fp32 accumulator truncates (measured: the dot product comes out low by up to 1.3e-5 relative after
+// the 432 chained MMAs of one F16X3 output, profiles/accuracy_r1.txt).  Here the MMA warp closes an accumulator
+// stage every `chunk_kb` K-slices and EIGHT epilogue warps add the chunks into fp32 registers with
+// round-to-nearest (128 running sums per thread; 168 registers per thread at 384 threads fill the register file),
+// so a truncating chain is only chunk_kb * 4 * nseg MMAs long.  TMEM stages alternate per chunk, so the
+// register adds of chunk c overlap the MMAs of chunk c + 1.
+// =====================================================================================================
+constexpr int kEpiWarpsC = 8;
+constexpr int kThreadsC = 128 + 32 * kEpiWarpsC;
+constexpr int kPitchC = 17;                      // floats; padded 32 x 16 transpose tile (fallback store path)
+
+struct GemmCfgC {
+  static constexpr int kStages = 4;
+  static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kEpiTileBytes = 2560;   // 32 x 16 fp32 (2 KB, SWIZZLE_64B) / 32 x 17 padded (2176 B)
+  static constexpr uint32_t kEpiColBytes = 2 * 128 * 4;
+  static constexpr uint32_t kEpiWarpBytes = 4096;   // keeps every warp's tile 1024-byte aligned
+  static constexpr uint32_t kEpiBytes = kEpiWarpsC * kEpiWarpBytes;
+  static constexpr uint32_t kBarBytes = 256;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static_assert(kEpiTileBytes + kEpiColBytes <= kEpiWarpBytes, "epilogue smem carve");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kThreadsC, 1)
+distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                            const __grid_constant__ CUtensorMap tm_out, const GemmParams p, const int chunk_kb) {
+  using Cfg = GemmCfgC;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_b_hi);
+    if (p.nseg == 3) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+    if (p.tma_store) tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiWarpsC * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_chunks = (p.num_kb + chunk_kb - 1) / chunk_kb;
+
+  if (warp < 4) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int total_kb = p.num_kb * p.nseg;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+          const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+          for (int kb = 0; kb < total_kb; ++kb) {
+            const int kk = kb / p.nseg, seg = kb - kk * p.nseg;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d((seg == 2) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], smem_a + stage * Cfg::kABytes, kk * BLOCK_K,
+                        m_blk * BLOCK_M);
+            tma_load_2d((seg == 1) ? &tm_b_lo : &tm_b_hi, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kk * BLOCK_K,
+                        n_blk * BLOCK_N);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (elect_one()) {
+        const uint32_t idesc = p.idesc;
+        int stage = 0;
+        uint32_t phase = 0;
+        int ci = 0;   // chunk counter over the whole kernel: TMEM stage = ci & 1
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+          for (int c = 0; c < num_chunks; ++c, ++ci) {
+            const int acc = ci & 1;
+            mbar_wait(&tmem_empty_bar[acc], ((ci >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            const int kb_end = min(p.num_kb, (c + 1) * chunk_kb) * p.nseg;
+            for (int kb = c * chunk_kb * p.nseg; kb < kb_end; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+              const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != c * chunk_kb * p.nseg) || k != 0);
+              umma_commit<1>(&empty_bar[stage]);
+              if (kb == kb_end - 1) umma_commit<1>(&tmem_full_bar[acc]);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: 8 warps, thread = (row, 128-column half) =====================
+    const int ew = warp - 4;
+    const int quarter = ew & 3;                    // TMEM lane quarter == warp % 4
+    const int half = ew >> 2;                      // columns [128 * half, 128 * half + 128)
+    uint8_t* my_epi = smem_epi + ew * Cfg::kEpiWarpBytes;
+    float* tile = reinterpret_cast<float*>(my_epi);
+    float* col_rg = reinterpret_cast<float*>(my_epi + Cfg::kEpiTileBytes);   // [128]
+    float* col_sg = col_rg + 128;                                            // [128]
+    int ci = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int col0 = n_blk * BLOCK_N + half * 128;
+      const int my_row = row0 + lane;
+      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : 1.0f;
+      const float coef_row = p.alpha * ((p.sq != nullptr && my_row < p.Q) ? p.sq[my_row] : 1.0f);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = col0 + j * 32 + lane;
+        col_rg[j * 32 + lane] = (p.rg != nullptr && col < p.G) ? p.rg[col] : 0.0f;
+        col_sg[j * 32 + lane] = (p.sg != nullptr && col < p.G) ? p.sg[col] : 1.0f;
+      }
+      __syncwarp();
+      float r[128];
+      for (int c = 0; c < num_chunks; ++c, ++ci) {
+        const int acc = ci & 1;
+        mbar_wait(&tmem_full_bar[acc], (ci >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BLOCK_N + half * 128 + (uint32_t(quarter * 32) << 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + j * 32, v);
+          tmem_ld_wait();
+          if (c == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[j * 32 + i] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[j * 32 + i] = __fadd_rn(r[j * 32 + i], __uint_as_float(v[i]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (row0 >= p.Q || (p.debug & 1)) continue;
+      // d = fma(coef * sg, sum, rq + rg), 16 columns at a time
+#pragma unroll
+      for (int s16 = 0; s16 < 8; ++s16) {
+        const int cbase = col0 + s16 * 16;
+        if (cbase >= p.G) break;                 // warp-uniform
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          o[i] = __fmaf_rn(coef_row * col_sg[s16 * 16 + i], r[s16 * 16 + i], __fadd_rn(rq_row, col_rg[s16 * 16 + i]));
+        if (p.tma_store) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          // 32 rows x 64 bytes, SWIZZLE_64B: 16-byte chunk k of row r lives at chunk k ^ ((r >> 1) & 3)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tile) + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, tile, cbase, row0);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tile[lane * kPitchC + i] = o[i];
+          __syncwarp();
+          const int cl = lane & 15, rh = lane >> 4;          // 2 rows x 16 columns per instruction
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr += 2) {
+            const int row = row0 + rr + rh, col = cbase + cl;
+            if (row < p.Q && col < p.G) p.out[(int64_t)row * p.ldo + col] = tile[(rr + rh) * kPitchC + cl];
+          }
+        }
+      }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -294,9 +520,9 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // row-major [rows, cols] matrix of `esize`-byte elements -> tiles of box_rows x box_cols, 128-byte swizzle
-// (box_cols * esize == 128), zero fill / clipping out of bounds.
+// (box_cols * esize == swizzle span), zero fill / clipping out of bounds.
 static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
-                     int64_t pitch_elems, int box_rows, int box_cols) {
+                     int64_t pitch_elems, int box_rows, int box_cols, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -307,7 +533,7 @@ static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const v
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld pitch=%lld)", (int)r, (long long)rows,
               (long long)cols, (long long)pitch_elems);
@@ -384,8 +610,67 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   return IEEE_OK;
 }
 
+static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                               int precision, float* out, int64_t ldo, cudaStream_t stream, int chunk_kb) {
+  using Cfg = GemmCfgC;
+  PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
+  const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
+  const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
+  const CUtensorMapDataType dt16 = CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
+  int rc;
+  if ((rc = make_tmap(&ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, BLOCK_N, BLOCK_K))) return rc;
+  if (precision == IEEE_PREC_F16X3) {
+    if ((rc = make_tmap(&ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, BLOCK_N, BLOCK_K))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  GemmParams p;
+  const bool euclid = metric == IEEE_METRIC_EUCLIDEAN;
+  p.rq = euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr;
+  p.rg = euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr;
+  p.sq = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(qb + lq.scale_off) : nullptr;
+  p.sg = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(gb + lg.scale_off) : nullptr;
+  p.alpha = euclid ? -2.0f : -1.0f;
+  p.out = out;
+  p.ldo = ldo;
+  p.Q = (int)Q;
+  p.G = (int)G;
+  p.num_kb = (int)(lq.Dp / BLOCK_K);
+  p.nseg = precision == IEEE_PREC_F16X3 ? 3 : 1;
+  p.num_m_tiles = (int)((Q + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
+  p.idesc = umma_idesc_16bit(BLOCK_M, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
+  p.debug = g_debug_flags;
+  p.tma_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 && !(g_debug_flags & 4)) ? 1 : 0;
+  if (p.tma_store) {
+    if ((rc = make_tmap(&t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, Q, G, ldo, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  } else {
+    t_out = ta_hi;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  distmat_umma_chunked_kernel<<<grid, kThreadsC, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, t_out, p, chunk_kb);
+  count_launch();
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
                  float* out, int64_t ldo, cudaStream_t stream, int cta_group) {
+  // chunked accumulation serves the fp32-grade mode; the 1-pass BF16 mode keeps the whole K in TMEM (throughput mode)
+  if (cta_group == 1 && g_accum_chunk_kb > 0 && (precision == IEEE_PREC_F16X3 || (g_debug_flags & 8)))
+    return launch_umma_chunked(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
   if (cta_group == 2)
     return launch_umma<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);
   return launch_umma<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);

@@ -67,18 +67,21 @@ class RetrievalEvaluator:
         _lib.require_cuda()
         if dist_metric not in _lib.METRICS:
             raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(dist_metric))
-        self.device = gf.device
+        self.device = gf.device if gf is not None else torch.device("cuda", torch.cuda.current_device())
         self.metric, self.normalize = dist_metric, normalize_feature
-        self.precision = precision or ("bf16" if gf.dtype == torch.bfloat16 else "f16x3")
+        self.precision = precision or ("bf16" if gf is not None and gf.dtype == torch.bfloat16 else "f16x3")
         self.max_rank = max_rank
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.g_offset = g_offset
         self.block_bytes = block_bytes
         with torch.cuda.device(self.device):
-            self.gallery = PackedFeatures(gf, dist_metric, normalize_feature, self.precision)
+            # the gallery as packed row chunks [(first row, PackedFeatures)]: one chunk when the features are already
+            # in HBM, several when they are streamed from the host (from_host) so that the contraction of chunk i
+            # overlaps the PCIe copy of chunk i + 1
+            self.chunks = [(0, PackedFeatures(gf, dist_metric, normalize_feature, self.precision))] if gf is not None else []
             self.labels = GalleryLabels(g_pids, g_camids, self.device)
-        self.G = self.gallery.rows
+        self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
         self._side = None
@@ -108,10 +111,45 @@ class RetrievalEvaluator:
                   self.max_rank, ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
         return st
 
+    @classmethod
+    def from_host(cls, gf_host: torch.Tensor, g_pids, g_camids, dist_metric="euclidean", normalize_feature=False,
+                  precision=None, max_rank=20, num_chunks=4, device=None, **kw):
+        """Gallery features in (pinned) host memory: the copy is split into row chunks on a copy stream; each chunk is
+        packed and multiplied as soon as it lands, so PCIe time and tensor-core time overlap."""
+        _lib.require_cuda()
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self = cls(None, g_pids, g_camids, dist_metric, normalize_feature,
+                   precision or ("bf16" if gf_host.dtype == torch.bfloat16 else "f16x3"), max_rank, **kw)
+        G = gf_host.shape[0]
+        assert G == self.G
+        step = max(256, ((G + num_chunks - 1) // num_chunks + 255) // 256 * 256)     # whole 256-column tiles per chunk
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            self._copy = torch.cuda.Stream(device=dev)
+            self._copy.wait_stream(main)
+            for c0 in range(0, G, step):
+                c1 = min(G, c0 + step)
+                staged = torch.empty((c1 - c0, gf_host.shape[1]), dtype=gf_host.dtype, device=dev)
+                with torch.cuda.stream(self._copy):
+                    staged.copy_(gf_host[c0:c1], non_blocking=True)
+                    ev = self._copy.record_event()
+                self.chunks.append((c0, (ev, staged)))
+        return self
+
     def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False):
-        """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank."""
+        """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
+        `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
         with torch.cuda.device(self.device):
             Q = qf.shape[0]
+            q_event = None
+            if not qf.is_cuda:
+                copy = getattr(self, "_copy", None) or torch.cuda.Stream(device=self.device)
+                q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
+                copy.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy):
+                    q_dev.copy_(qf, non_blocking=True)
+                    q_event = copy.record_event()
+                qf = q_dev
             qp = _as_device(q_pids, torch.int64, self.device)
             qc = _as_device(q_camids, torch.int64, self.device)
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
@@ -126,8 +164,21 @@ class RetrievalEvaluator:
                 self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
 
             def contraction(s, e):
-                qpk = PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
-                return packed_distmat(qpk, self.gallery, self._block[: e - s])
+                qpk = qf_packed(s, e)
+                out = self._block[: e - s]
+                for i, (c0, gpk) in enumerate(self.chunks):
+                    if isinstance(gpk, tuple):            # (event, host->device staging tensor): pack on arrival
+                        ev, staged = gpk
+                        torch.cuda.current_stream().wait_event(ev)
+                        gpk = PackedFeatures(staged, self.metric, self.normalize, self.precision)
+                        self.chunks[i] = (c0, gpk)        # packed once, reused by later query blocks
+                    packed_distmat(qpk, gpk, out[:, c0: c0 + gpk.rows])
+                return out
+
+            def qf_packed(s, e):
+                if q_event is not None:
+                    torch.cuda.current_stream().wait_event(q_event)
+                return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
 
             # list capacity: queried on a side stream; the first block's contraction is queued before the host
             # waits for it, so the round trip costs no GPU time
@@ -175,13 +226,18 @@ def evaluate(qf, gf, q_pids, g_pids, q_camids, g_camids, dist_metric="euclidean"
     tools/parse_test_res.py:70 parses, and returns (cmc, mAP)."""
     _lib.require_cuda()
     dev = qf.device if qf.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    qf = qf.to(dev, non_blocking=True)
-    gf = gf.to(dev, non_blocking=True)
+    streamed = (not rerank) and (not gf.is_cuda)
+    if not streamed:
+        qf = qf.to(dev, non_blocking=True)
+        gf = gf.to(dev, non_blocking=True)
     if verbose and normalize_feature:
         print("Normalzing features with L2 norm ...")
     if verbose:
         print("Computing distance matrix with metric={} ...".format(dist_metric))
-    if not rerank:
+    if streamed:
+        ev = RetrievalEvaluator.from_host(gf, g_pids, g_camids, dist_metric, normalize_feature, precision, max_rank)
+        cmc, mAP, _ = ev.evaluate(qf, q_pids, q_camids)
+    elif not rerank:
         ev = RetrievalEvaluator(gf, g_pids, g_camids, dist_metric, normalize_feature, precision, max_rank)
         cmc, mAP, _ = ev.evaluate(qf, q_pids, q_camids)
     else:

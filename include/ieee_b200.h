@@ -67,8 +67,14 @@ int ieee_device_info(int* sm_count, int* compute_capability);
 /* Tensor-core kernel pairing: 1 (default) = tcgen05 cta_group::1, one 128 x 256 tile per SM;
  * 2 = cta_group::2, one 256 x 256 tile per SM pair.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
 int ieee_set_cta_group(int cta_group);
+/* Accumulation chunking of the tensor-core contraction (cta_group 1): the tcgen05 fp32 accumulator truncates, so
+ * every `k_slices` 64-wide K-slices the partial sums are moved to registers and added there with round-to-nearest.
+ * 0 = accumulate the whole K in TMEM (fastest, ~1e-5 relative bias on the dot product); default 4 (F16X3 mode;
+ * the 1-pass BF16 mode always accumulates the whole K in TMEM).
+ * Returns the previous value. */
+int ieee_set_accum_chunk(int k_slices);
 /* Diagnostics for kernel tuning (results are WRONG when non-zero): bit 0 = tensor-core epilogue skips its global
- * stores, bit 1 = epilogue also skips the TMEM reads.  Returns the previous value. */
+ * stores, bit 1 = epilogue also skips the TMEM reads, bit 2 = no TMA store, bit 3 = chunk BF16 mode too.  Returns the previous value. */
 int ieee_set_debug_flags(int flags);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
 int64_t ieee_launch_count(void);

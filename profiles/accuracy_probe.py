@@ -31,7 +31,12 @@ def main():
         truth = R.distance_fp64(s.qf, s.gf).numpy()
         scale = ((s.qf.double() ** 2).sum(1, keepdim=True) + (s.gf.double() ** 2).sum(1, keepdim=True).t()).numpy()
         rows = {"torch_cpu_fp32 (reference)": R.compute_distance_matrix(s.qf, s.gf).numpy()}
-        for prec in ("f16x3", "bf16", "fp32_simt"):
+        from ieee_b200 import _lib
+        for chunk in (0, 9, 4, 2, 1):
+            _lib.load().ieee_set_accum_chunk(chunk)
+            rows[f"f16x3 accum_chunk={chunk}"] = compute_distance_matrix(s.qf.cuda(), s.gf.cuda(), "euclidean", precision="f16x3").cpu().numpy()
+        _lib.load().ieee_set_accum_chunk(4)
+        for prec in ("bf16", "fp32_simt"):
             rows[prec] = compute_distance_matrix(s.qf.cuda(), s.gf.cuda(), "euclidean", precision=prec).cpu().numpy()
         print("==", name)
         for k, v in rows.items():

@@ -50,3 +50,15 @@ def test_engine_prints_reference_lines(capsys):
     assert "mAP: {:.2%}".format(mAP) in out and "Rank-1  : {:.2%}".format(cmc[0]) in out
     with pytest.raises(ValueError):
         evaluate(s.qf, s.gf, s.q_pids, s.g_pids, s.q_camids, s.g_camids, dist_metric="manhattan")
+
+
+def test_streamed_host_gallery_equals_resident():
+    """RetrievalEvaluator.from_host (chunked PCIe copy overlapped with the contraction) == device-resident path."""
+    s = make_retrieval_set(260, 1500, 30, 4, dim=256, sigma=2.5, seed=44)
+    res = RetrievalEvaluator(s.gf.cuda(), s.g_pids, s.g_camids)
+    c1, m1, i1 = res.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True)
+    host = RetrievalEvaluator.from_host(s.gf.pin_memory(), s.g_pids, s.g_camids, num_chunks=3)
+    c2, m2, i2 = host.evaluate(s.qf.pin_memory(), s.q_pids, s.q_camids, return_distmat=True)
+    assert torch.equal(i1["distmat"], i2["distmat"]) and np.array_equal(c1, c2) and m1 == m2
+    c3, m3 = evaluate(s.qf, s.gf, s.q_pids, s.g_pids, s.q_camids, s.g_camids, verbose=False)      # pageable host tensors
+    assert np.array_equal(c1, c3) and m1 == m3
