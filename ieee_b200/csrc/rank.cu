@@ -325,7 +325,7 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
   for (int g = head + 4 * nvec + tid; g < G; g += kCountThreads) count_visit<MODE>(c, row[g], (uint32_t)g);
 }
 
-__global__ void __launch_bounds__(kCountThreads)
+__global__ void __launch_bounds__(kCountThreads, 6)
 rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
                   int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
                   const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,

@@ -22,6 +22,36 @@ from .utils.rerank import re_ranking_device
 DEFAULT_BLOCK_BYTES = 4 << 30   # HBM scratch for one distance block
 
 
+class Trace:
+    """CUDA-event timeline of one evaluation (IEEE_B200_TRACE=1): mark() records an event on the current stream,
+    report() -- after a synchronize -- lists the GPU time of every mark relative to the first and the host time at
+    which it was enqueued.  The reference only has wall-clock AverageMeters (engine.py:365-367)."""
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get("IEEE_B200_TRACE", "0") == "1"
+        self.marks = []
+
+    def mark(self, name: str):
+        if self.enabled:
+            import time
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev, time.perf_counter()))
+
+    def report(self):
+        if not self.enabled or not self.marks:
+            return
+        torch.cuda.synchronize()
+        _, e0, t0 = self.marks[0]
+        for name, ev, t in self.marks:
+            print("[trace] %-28s gpu %8.3f ms   enqueued at %8.3f ms" % (name, e0.elapsed_time(ev), (t - t0) * 1e3))
+        self.marks = []
+
+
+TRACE = Trace()
+
+
 def shard_bounds(num_rows: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous gallery slice of ``rank``: [start, stop).  Global index = local index + start, so the
     (distance, index) tie order is the same as on one GPU."""
@@ -85,6 +115,8 @@ class RetrievalEvaluator:
         self.g_total = self.G if g_total is None else g_total
         self._block = None
         self._side = None
+        self._copy = None
+        self._host_gallery = None
 
     # -- one query block ---------------------------------------------------------------------------------
     def _block_rows(self, Q: int) -> int:
@@ -113,45 +145,54 @@ class RetrievalEvaluator:
 
     @classmethod
     def from_host(cls, gf_host: torch.Tensor, g_pids, g_camids, dist_metric="euclidean", normalize_feature=False,
-                  precision=None, max_rank=20, num_chunks=4, device=None, **kw):
+                  precision=None, max_rank=20, num_chunks=8, device=None, **kw):
         """Gallery features in (pinned) host memory: the copy is split into row chunks on a copy stream; each chunk is
         packed and multiplied as soon as it lands, so PCIe time and tensor-core time overlap."""
         _lib.require_cuda()
         dev = device or torch.device("cuda", torch.cuda.current_device())
-        self = cls(None, g_pids, g_camids, dist_metric, normalize_feature,
-                   precision or ("bf16" if gf_host.dtype == torch.bfloat16 else "f16x3"), max_rank, **kw)
-        G = gf_host.shape[0]
-        assert G == self.G
-        step = max(256, ((G + num_chunks - 1) // num_chunks + 255) // 256 * 256)     # whole 256-column tiles per chunk
         with torch.cuda.device(dev):
-            main = torch.cuda.current_stream()
-            self._copy = torch.cuda.Stream(device=dev)
-            self._copy.wait_stream(main)
-            for c0 in range(0, G, step):
-                c1 = min(G, c0 + step)
-                staged = torch.empty((c1 - c0, gf_host.shape[1]), dtype=gf_host.dtype, device=dev)
-                with torch.cuda.stream(self._copy):
-                    staged.copy_(gf_host[c0:c1], non_blocking=True)
-                    ev = self._copy.record_event()
-                self.chunks.append((c0, (ev, staged)))
+            self = cls(None, g_pids, g_camids, dist_metric, normalize_feature,
+                       precision or ("bf16" if gf_host.dtype == torch.bfloat16 else "f16x3"), max_rank, **kw)
+        assert gf_host.shape[0] == self.G
+        self._host_gallery, self._num_chunks = gf_host, num_chunks      # copies start in evaluate(), after the queries'
         return self
+
+    def _start_gallery_copies(self, copy: torch.cuda.Stream):
+        gf_host, G = self._host_gallery, self.G
+        step = max(256, ((G + self._num_chunks - 1) // self._num_chunks + 255) // 256 * 256)   # whole 256-column tiles
+        for c0 in range(0, G, step):
+            c1 = min(G, c0 + step)
+            staged = torch.empty((c1 - c0, gf_host.shape[1]), dtype=gf_host.dtype, device=self.device)
+            with torch.cuda.stream(copy):
+                staged.copy_(gf_host[c0:c1], non_blocking=True)
+                ev = copy.record_event()
+            self.chunks.append((c0, (ev, staged)))
+        self._host_gallery = None
 
     def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False):
         """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
         `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
         with torch.cuda.device(self.device):
+            TRACE.mark("evaluate: start")
             Q = qf.shape[0]
-            q_event = None
-            if not qf.is_cuda:
-                copy = getattr(self, "_copy", None) or torch.cuda.Stream(device=self.device)
-                q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
-                copy.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(copy):
-                    q_dev.copy_(qf, non_blocking=True)
-                    q_event = copy.record_event()
-                qf = q_dev
+            # small label copies go FIRST: host->device transfers of every stream share one copy engine queue, so a
+            # label copy issued after the feature copies would hold the compute stream until they have all landed
             qp = _as_device(q_pids, torch.int64, self.device)
             qc = _as_device(q_camids, torch.int64, self.device)
+            q_event = None
+            pending_gallery = getattr(self, "_host_gallery", None) is not None
+            if not qf.is_cuda or pending_gallery:
+                if self._copy is None:
+                    self._copy = torch.cuda.Stream(device=self.device)
+                self._copy.wait_stream(torch.cuda.current_stream())
+                if not qf.is_cuda:                       # queries first: every contraction needs them
+                    q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
+                    with torch.cuda.stream(self._copy):
+                        q_dev.copy_(qf, non_blocking=True)
+                        q_event = self._copy.record_event()
+                    qf = q_dev
+                if pending_gallery:
+                    self._start_gallery_copies(self._copy)
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
@@ -173,6 +214,7 @@ class RetrievalEvaluator:
                         gpk = PackedFeatures(staged, self.metric, self.normalize, self.precision)
                         self.chunks[i] = (c0, gpk)        # packed once, reused by later query blocks
                     packed_distmat(qpk, gpk, out[:, c0: c0 + gpk.rows])
+                    TRACE.mark("  chunk %d contraction" % c0)
                 return out
 
             def qf_packed(s, e):
@@ -185,7 +227,9 @@ class RetrievalEvaluator:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             cap_done, cap_host = self.labels.list_cap_async(qp, self._side)
+            TRACE.mark("list_cap queued")
             dist = contraction(0, min(Q, rows))
+            TRACE.mark("contraction(block 0) done")
             cap_done.synchronize()
             cap = max(int(cap_host.item()), 1)
             if self.world > 1:
@@ -207,11 +251,14 @@ class RetrievalEvaluator:
             k_eff = min(self.max_rank, self.g_total)
             cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
             summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
+            TRACE.mark("rank stages done")
             _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
                       cmc.data_ptr(), summ.data_ptr(), _lib.stream())
+            TRACE.mark("reduce done")
             out = torch.cat([cmc.view(torch.uint8), summ]).cpu().numpy()          # one D2H copy, synchronises
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
             summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff:].tobytes())
+        TRACE.report()
         raise_for_status(summary, self.max_rank)
         info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first}
         if return_distmat:
