@@ -265,7 +265,7 @@ __device__ __forceinline__ int exact_bin(CountCtx& c, int lo, int n, uint64_t pe
 // Branch-free per-element body (the lanes of a warp must stay converged over the 16 elements in flight): every
 // element increments exactly one counter -- bin 0 if it precedes all thresholds, the trash bin R + 1 if it follows
 // them (or is NaN), else its bin from the cell table; only cells that hold a threshold take a (reconverging) branch.
-template <int MODE>
+template <int MODE, int NT>
 __device__ __forceinline__ void count_visit(CountCtx& c, float d, uint32_t g) {
   int b;
   if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
@@ -289,40 +289,161 @@ __device__ __forceinline__ void count_visit(CountCtx& c, float d, uint32_t g) {
     if (!is_thr) c.ties += same;
     b = (ke > c.kmax) ? c.trash : a;
   }
-  if constexpr (MODE == COUNT_LUT_PRIVATE) c.priv[b * kCountThreads] += 1;
+  if constexpr (MODE == COUNT_LUT_PRIVATE) c.priv[b * NT] += 1;
   else atomicAdd(&c.hist[b], 1);
 }
 
-template <int MODE>
-__device__ __forceinline__ void count_stream(CountCtx& c, const float* __restrict__ row, int G) {
-  const int tid = threadIdx.x;
+// NT threads (a CTA or one warp) stream one row; `tid` is the thread's index among them.
+template <int MODE, int NT>
+__device__ __forceinline__ void count_stream(CountCtx& c, const float* __restrict__ row, int G, int tid) {
   const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
   int head = (int)(((16 - (addr & 15)) & 15) >> 2);
   if (head > G) head = G;
-  for (int g = tid; g < head; g += kCountThreads) count_visit<MODE>(c, row[g], (uint32_t)g);
+  for (int g = tid; g < head; g += NT) count_visit<MODE, NT>(c, row[g], (uint32_t)g);
   const int nvec = (G - head) >> 2;
   const float4* rv = reinterpret_cast<const float4*>(row + head);
   int i = tid;
   if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
-    for (; i + 3 * kCountThreads < nvec; i += 4 * kCountThreads) {   // 4 independent 16-byte loads in flight
-      const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + kCountThreads), a2 = __ldcs(rv + i + 2 * kCountThreads),
-                   a3 = __ldcs(rv + i + 3 * kCountThreads);
+    for (; i + 3 * NT < nvec; i += 4 * NT) {   // 4 independent 16-byte loads in flight
+      const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + NT), a2 = __ldcs(rv + i + 2 * NT), a3 = __ldcs(rv + i + 3 * NT);
       uint32_t g0 = (uint32_t)(head + 4 * i);
-      count_visit<MODE>(c, a0.x, g0); count_visit<MODE>(c, a0.y, g0 + 1); count_visit<MODE>(c, a0.z, g0 + 2); count_visit<MODE>(c, a0.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      count_visit<MODE>(c, a1.x, g0); count_visit<MODE>(c, a1.y, g0 + 1); count_visit<MODE>(c, a1.z, g0 + 2); count_visit<MODE>(c, a1.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      count_visit<MODE>(c, a2.x, g0); count_visit<MODE>(c, a2.y, g0 + 1); count_visit<MODE>(c, a2.z, g0 + 2); count_visit<MODE>(c, a2.w, g0 + 3);
-      g0 += 4 * kCountThreads;
-      count_visit<MODE>(c, a3.x, g0); count_visit<MODE>(c, a3.y, g0 + 1); count_visit<MODE>(c, a3.z, g0 + 2); count_visit<MODE>(c, a3.w, g0 + 3);
+      count_visit<MODE, NT>(c, a0.x, g0); count_visit<MODE, NT>(c, a0.y, g0 + 1); count_visit<MODE, NT>(c, a0.z, g0 + 2); count_visit<MODE, NT>(c, a0.w, g0 + 3);
+      g0 += 4 * NT;
+      count_visit<MODE, NT>(c, a1.x, g0); count_visit<MODE, NT>(c, a1.y, g0 + 1); count_visit<MODE, NT>(c, a1.z, g0 + 2); count_visit<MODE, NT>(c, a1.w, g0 + 3);
+      g0 += 4 * NT;
+      count_visit<MODE, NT>(c, a2.x, g0); count_visit<MODE, NT>(c, a2.y, g0 + 1); count_visit<MODE, NT>(c, a2.z, g0 + 2); count_visit<MODE, NT>(c, a2.w, g0 + 3);
+      g0 += 4 * NT;
+      count_visit<MODE, NT>(c, a3.x, g0); count_visit<MODE, NT>(c, a3.y, g0 + 1); count_visit<MODE, NT>(c, a3.z, g0 + 2); count_visit<MODE, NT>(c, a3.w, g0 + 3);
     }
   }
-  for (; i < nvec; i += kCountThreads) {
+  for (; i < nvec; i += NT) {
     const float4 a = __ldcs(rv + i);
     const uint32_t g0 = (uint32_t)(head + 4 * i);
-    count_visit<MODE>(c, a.x, g0); count_visit<MODE>(c, a.y, g0 + 1); count_visit<MODE>(c, a.z, g0 + 2); count_visit<MODE>(c, a.w, g0 + 3);
+    count_visit<MODE, NT>(c, a.x, g0); count_visit<MODE, NT>(c, a.y, g0 + 1); count_visit<MODE, NT>(c, a.z, g0 + 2); count_visit<MODE, NT>(c, a.w, g0 + 3);
   }
-  for (int g = head + 4 * nvec + tid; g < G; g += kCountThreads) count_visit<MODE>(c, row[g], (uint32_t)g);
+  for (int g = head + 4 * nvec + tid; g < G; g += NT) count_visit<MODE, NT>(c, row[g], (uint32_t)g);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// count, warp-per-query variant: for short rows (G <= 64K) the per-CTA setup of rank_count_kernel (sort, cell
+// table, zeroing and folding 256 private columns, ~8000 warp instructions) costs more than streaming the row.
+// Here every warp owns one query and does its setup with warp-level primitives only (~500 instructions);
+// eight queries per CTA.  Needs R <= 64 thresholds and finite threshold distances, else the warp falls back to
+// the generic search with shared atomics on its own histogram.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWarpQ = 8;            // queries (warps) per CTA
+constexpr int kWarpRmax = 64;        // thresholds per query the private table holds
+__host__ __device__ inline int warp_smem_per_query(int rmax) {   // T[rmax] u64 | hist[rmax + 2] | cell[1024] | priv[rmax + 2][32]
+  return ((rmax * 8 + (rmax + 2) * 4 + kLutCells * 4 + (rmax + 2) * 32 * 4) + 15) & ~15;
+}
+
+__global__ void __launch_bounds__(32 * kWarpQ)
+rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
+                       int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
+                       const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
+                       unsigned long long* __restrict__ ties_out) {
+  extern __shared__ __align__(16) uint8_t ws_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint8_t* mine = ws_raw + size_t(w) * warp_smem_per_query(rmax);
+  uint64_t* T = reinterpret_cast<uint64_t*>(mine);                                   // [rmax]
+  int32_t* hist = reinterpret_cast<int32_t*>(mine + rmax * 8);                        // [rmax + 2]
+  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + rmax + 2);                      // [1024]
+  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells);                       // [rmax + 2][32]
+  const int64_t q = (int64_t)blockIdx.x * kWarpQ + w;
+  if (q >= Q) return;
+  const int stride = shards * cap + 1;
+  int32_t* out = counts + q * stride;
+  const int nj = n_junk[q];
+  // thresholds of all shards, staged in `priv` (not live yet)
+  uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
+  int R = 0;
+  for (int s = 0; s < shards; ++s) {
+    const int n = n_rel_all[(int64_t)s * Q + q];
+    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * cap;
+    for (int i = lane; i < n; i += 32) Tin[R + i] = src[i];
+    R += n;
+  }
+  if (lane == 0) out[stride - 1] = nj;
+  if (R == 0) return;                       // invalid query (rank.py:142-144)
+  __syncwarp();
+  // rank sort (keys are distinct)
+  for (int k = lane; k < R; k += 32) {
+    const uint64_t me = Tin[k];
+    int pos = 0;
+    for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
+    T[pos] = me;
+  }
+  for (int i = lane; i < kLutCells; i += 32) cell[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
+  for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;     // own column only: i % 32 == lane
+  const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
+  const float lo = key_to_float(kmin), hi = key_to_float(kmax);
+  const float span = hi - lo;
+  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
+  const float scale = use_lut ? ((float)kLutCells - 0.5f) / span : 0.f;
+  if (use_lut) {
+    for (int k = lane; k < R; k += 32) {
+      const float d = key_to_float((uint32_t)(T[k] >> 32));
+      atomicAdd(&cell[(int)((d - lo) * scale) & (kLutCells - 1)], 1u << 20);
+    }
+    __syncwarp();
+    // exclusive scan over the 1024 cells, 32 at a time (lane <-> cell: conflict-free), carry in a register
+    int carry = 0;
+    for (int k0 = 0; k0 < kLutCells; k0 += 32) {
+      const int cnt = (int)(cell[k0 + lane] >> 20);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+      cell[k0 + lane] = (uint32_t)(carry + incl - cnt) | ((uint32_t)cnt << 20);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncwarp();
+  CountCtx c;
+  c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + lane;
+  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1;
+  c.g_offset = (uint32_t)g_offset; c.ties = 0;
+  const float* row = distmat + q * ld;
+  if (use_lut) count_stream<COUNT_LUT_PRIVATE, 32>(c, row, G, lane);
+  else count_stream<COUNT_SEARCH_ATOMIC, 32>(c, row, G, lane);
+  int tie_local = c.ties;
+  __syncwarp();
+  if (use_lut) {   // fold: lane l sums bins l and l + 32 over the 32 private columns (rotated reads: conflict-free)
+    for (int b = lane; b <= R; b += 32) {
+      int sum = 0;
+      for (int j = 0; j < 32; ++j) sum += priv[b * 32 + ((j + lane) & 31)];
+      hist[b] = sum;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < nj; i += 32) {      // junk items were streamed too: take them out (rank.py:136-140)
+    const uint64_t pe = junk[q * cap + i];
+    const uint32_t ke = (uint32_t)(pe >> 32);
+    if (ke > kmax) continue;
+    int a = 0, e = R;
+    while (a < e) { const int m = (a + e) >> 1; if (T[m] < pe) a = m + 1; else e = m; }
+    for (int j = a; j < R && (uint32_t)(T[j] >> 32) == ke; ++j) tie_local--;
+    for (int j = a - 1; j >= 0 && (uint32_t)(T[j] >> 32) == ke; --j) tie_local--;
+    atomicSub(&hist[a], 1);
+  }
+  for (int o = 16; o > 0; o >>= 1) tie_local += __shfl_xor_sync(0xffffffffu, tie_local, o);
+  __syncwarp();
+  // counts[k] = sum_{b <= k} hist[b] - [T_k is a local row entry]
+  int carry = 0;
+  for (int base = 0; base < R; base += 32) {
+    const int k = base + lane;
+    const int v = k < R ? hist[k] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    if (k < R) {
+      const int64_t gi = (int64_t)(uint32_t)T[k] - g_offset;
+      out[k] = carry + incl - ((gi >= 0 && gi < G) ? 1 : 0);
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0 && ties_out != nullptr && tie_local != 0) atomicAdd(ties_out, (unsigned long long)(long long)tie_local);
 }
 
 __global__ void __launch_bounds__(kCountThreads, 6)
@@ -424,9 +545,9 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1;
   c.g_offset = (uint32_t)g_offset; c.ties = 0;
   const float* row = distmat + q * ld;
-  if (!use_lut) count_stream<COUNT_SEARCH_ATOMIC>(c, row, G);
-  else if (priv_ok) count_stream<COUNT_LUT_PRIVATE>(c, row, G);
-  else count_stream<COUNT_LUT_ATOMIC>(c, row, G);
+  if (!use_lut) count_stream<COUNT_SEARCH_ATOMIC, kCountThreads>(c, row, G, tid);
+  else if (priv_ok) count_stream<COUNT_LUT_PRIVATE, kCountThreads>(c, row, G, tid);
+  else count_stream<COUNT_LUT_ATOMIC, kCountThreads>(c, row, G, tid);
   int tie_local = c.ties;
   __syncthreads();
   if (use_lut && priv_ok) {   // fold the private counters: warp w sums bins w, w + 8, ...
@@ -481,6 +602,8 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   if (tid == 0 && ties_out != nullptr && misc[1] != 0) atomicAdd(ties_out, (unsigned long long)(long long)misc[1]);
 }
 
+int g_count_warp_max_g = 65536;   // rows up to this length use the warp-per-query kernel (ieee_set_debug_flags bit 4: off)
+
 size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(max(shards * cap, 2))).total; }
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
@@ -489,6 +612,20 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   IEEE_REQUIRE(distmat && rel_all && n_rel_all && junk && n_junk && counts, "rank_count: null pointer");
   IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
+  if (G <= g_count_warp_max_g && shards * cap <= kWarpRmax && !(g_debug_flags & 16)) {     // short rows: one warp per query
+    const int rmax = (shards * cap + 1) & ~1;      // even: keeps the 8-byte alignment of every query's T
+    const size_t wsmem = size_t(kWarpQ) * warp_smem_per_query(rmax);
+    static size_t wattr = 0;
+    if (wsmem > 48 * 1024 && wsmem > wattr) {
+      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      wattr = wsmem;
+    }
+    rank_count_warp_kernel<<<(unsigned)((Q + kWarpQ - 1) / kWarpQ), 32 * kWarpQ, wsmem, stream>>>(
+        distmat, ld, Q, (int)G, g_offset, shards, cap, rmax, rel_all, n_rel_all, junk, n_junk, counts, ties);
+    count_launch();
+    IEEE_CUDA_CHECK(cudaGetLastError());
+    return IEEE_OK;
+  }
   const int Rp = next_pow2(max(shards * cap, 2));
   const size_t smem = count_smem_plan(Rp).total;
   IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: shards*cap=%d relevant items per query exceed the shared-memory budget",

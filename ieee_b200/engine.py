@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .metrics.rank import GalleryLabels, RankStages, _as_device, raise_for_status
+from .metrics.rank import GalleryLabels, RankStages, _as_device, copy_stream, raise_for_status
 from .utils.rerank import re_ranking_device
 
 DEFAULT_BLOCK_BYTES = 4 << 30   # HBM scratch for one distance block
@@ -114,7 +114,6 @@ class RetrievalEvaluator:
         self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
-        self._side = None
         self._copy = None
         self._host_gallery = None
 
@@ -179,11 +178,12 @@ class RetrievalEvaluator:
             # label copy issued after the feature copies would hold the compute stream until they have all landed
             qp = _as_device(q_pids, torch.int64, self.device)
             qc = _as_device(q_camids, torch.int64, self.device)
+            ids_ready = torch.cuda.current_stream().record_event()
             q_event = None
             pending_gallery = getattr(self, "_host_gallery", None) is not None
             if not qf.is_cuda or pending_gallery:
                 if self._copy is None:
-                    self._copy = torch.cuda.Stream(device=self.device)
+                    self._copy = copy_stream(self.device)
                 self._copy.wait_stream(torch.cuda.current_stream())
                 if not qf.is_cuda:                       # queries first: every contraction needs them
                     q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
@@ -222,14 +222,12 @@ class RetrievalEvaluator:
                     torch.cuda.current_stream().wait_event(q_event)
                 return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
 
-            # list capacity: queried on a side stream; the first block's contraction is queued before the host
-            # waits for it, so the round trip costs no GPU time
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            cap_done, cap_host = self.labels.list_cap_async(qp, self._side)
-            TRACE.mark("list_cap queued")
+            # The contraction of the first block is queued FIRST; the list capacity is then queried on a side stream
+            # that only waits for the gallery grouping and the query ids, so its host round trip (and the host-side
+            # allocations below) hide behind the tensor-core kernel.
             dist = contraction(0, min(Q, rows))
-            TRACE.mark("contraction(block 0) done")
+            TRACE.mark("contraction(block 0) queued")
+            cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready)
             cap_done.synchronize()
             cap = max(int(cap_host.item()), 1)
             if self.world > 1:

@@ -21,6 +21,25 @@ def _as_device(x, dtype, device):
     return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype, non_blocking=True)
 
 
+# Per-device helpers that are expensive to create (cudaStreamCreate, cudaHostAlloc) and safe to share: the side
+# stream for the capacity query, the copy stream for host features, one pinned int32 for the read-back.
+_SIDE_STREAMS, _COPY_STREAMS, _PINNED_CAP = {}, {}, {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def copy_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
 class GalleryLabels:
     """Gallery ids on the device plus their pid-sorted grouping (built once, reused per query block)."""
 
@@ -33,22 +52,27 @@ class GalleryLabels:
         self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):
             _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
-        self._scratch = torch.zeros(64, dtype=torch.int32, device=device)
+            self._scratch = torch.zeros(64, dtype=torch.int32, device=device)
+            self.ready = torch.cuda.current_stream().record_event()      # grouping queued up to here
 
-    def list_cap_async(self, q_pids: torch.Tensor, side: torch.cuda.Stream):
-        """Start the capacity query on `side` (after the work already queued on the current stream) and return an
-        event + pinned int32; the caller keeps queueing the contraction on its own stream and reads the value when
-        it needs it, so the host round trip hides behind the GEMM."""
-        cur = torch.cuda.current_stream()
-        side.wait_stream(cur)
-        if not hasattr(self, "_cap_host"):
-            self._cap_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
+        """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
+        ids (`q_ready`) -- NOT after whatever else the compute stream holds, so the caller can queue the contraction
+        first and the host round trip hides behind it.  Returns (event, pinned int32)."""
+        dev = q_pids.device
+        side = side_stream(dev)
+        key = dev.index
+        if key not in _PINNED_CAP:
+            _PINNED_CAP[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        host = _PINNED_CAP[key]
+        side.wait_event(self.ready)
+        side.wait_event(q_ready)
         with torch.cuda.stream(side):
             _lib.call("ieee_rank_list_cap", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
                       self._scratch.data_ptr(), _lib.stream())
-            self._cap_host.copy_(self._scratch[:1], non_blocking=True)
+            host.copy_(self._scratch[:1], non_blocking=True)
             done = side.record_event()
-        return done, self._cap_host
+        return done, host
 
     def list_cap(self, q_pids: torch.Tensor) -> int:
         cap = C.c_int32(0)
