@@ -783,6 +783,93 @@ int rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, in
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTopkThreads = 256;
 constexpr int kTopkBuf = 2048;   // candidates; compaction keeps k <= kTopkBuf / 2
+constexpr int kTopkFastMaxK = 120;
+
+struct TopkArgs {
+  const float* row;
+  int64_t G, g_offset;
+  bool masked;
+  int64_t qp, qc;
+  const int64_t* g_pids;
+  const int64_t* g_camids;
+  int k;
+};
+
+// General path: threshold filter into the candidate buffer, compacted by a bitonic sort whenever the next tile
+// could overflow it.  Any k <= kTopkBuf / 2.  Returns the number of candidates left in cand[] (unsorted).
+__device__ int topk_stream_path(const TopkArgs& a, uint64_t* cand, int* count_s, uint64_t* tau_s) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { *count_s = 0; *tau_s = kPadKey; }
+  __syncthreads();
+  constexpr int kTile = kTopkThreads * 4;
+  for (int64_t g0 = 0; g0 < a.G; g0 += kTile) {
+    const uint64_t tau = *tau_s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t g = g0 + j * kTopkThreads + tid;
+      if (g < a.G) {
+        const uint64_t pe = pack_key(__ldcs(a.row + g), (uint32_t)(g + a.g_offset));
+        if (pe < tau) {
+          const bool is_junk = a.masked && a.g_pids[g] == a.qp && a.g_camids[g] == a.qc;   // rank.py:136
+          if (!is_junk) cand[atomicAdd(count_s, 1)] = pe;
+        }
+      }
+    }
+    __syncthreads();
+    const int filled = *count_s;             // snapshot taken between two barriers: every thread sees the same value
+    __syncthreads();                         // (without it fast threads would already be appending the next tile)
+    if (filled > kTopkBuf - kTile) {         // next tile could overflow: keep the k best, tighten the threshold
+      for (int i = filled + tid; i < kTopkBuf; i += kTopkThreads) cand[i] = kPadKey;
+      block_bitonic_sort(cand, kTopkBuf);
+      if (tid == 0) { *count_s = min(filled, a.k); if (filled >= a.k) *tau_s = cand[a.k - 1]; }
+      __syncthreads();
+    }
+  }
+  return *count_s;
+}
+
+// Fast path (k <= kTopkFastMaxK): every thread keeps the minimum packed key of its strided share of the row; the
+// m-th smallest of those 256 minima is >= the m-th smallest element of the row, so with m = 2k + 8 (head-room for
+// junk entries) it bounds the k-th smallest kept element unless more than k + 8 of the leaders are junk.  A second
+// pass over the (L2-resident) row collects the few elements below that bound.  Returns the candidate count, or -1
+// when the bound left fewer than k kept candidates / overflowed (the caller then takes the general path).
+__device__ int topk_select_path(const TopkArgs& a, uint64_t* cand, int* count_s) {
+  const int tid = threadIdx.x;
+  uint64_t best = kPadKey;
+  for (int64_t g = tid; g < a.G; g += kTopkThreads) {
+    const uint64_t pe = pack_key(a.row[g], (uint32_t)(g + a.g_offset));
+    best = pe < best ? pe : best;
+  }
+  cand[tid] = best;
+  if (tid == 0) *count_s = 0;
+  block_bitonic_sort(cand, kTopkThreads);
+  const int m = min(2 * a.k + 8, kTopkThreads) - 1;
+  const uint64_t tau = cand[m];
+  __syncthreads();
+  if (tau == kPadKey) return -1;             // fewer than m+1 populated threads (tiny rows): general path
+  const float tau_d = key_to_float((uint32_t)(tau >> 32));
+  for (int64_t g = tid; g < a.G; g += kTopkThreads) {
+    const float d = a.row[g];
+    if (!(d > tau_d)) {                      // cheap float pre-filter (NaN passes and is decided by the key compare)
+      const uint64_t pe = pack_key(d, (uint32_t)(g + a.g_offset));
+      if (pe <= tau) {
+        const bool is_junk = a.masked && a.g_pids[g] == a.qp && a.g_camids[g] == a.qc;
+        if (!is_junk) {
+          const int pos = atomicAdd(count_s, 1);
+          if (pos < kTopkBuf) cand[pos] = pe;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n = *count_s;
+  __syncthreads();
+  if (n > kTopkBuf) return -1;
+  // every kept element below the bound was collected; fewer than k of them means the bound was spent on junk
+  // (or the row has fewer than k kept entries in total, which only the general path can tell)
+  if (n < a.k) return -1;
+  return n;
+}
 
 __global__ void __launch_bounds__(kTopkThreads)
 topk_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset,
@@ -793,37 +880,22 @@ topk_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
   __shared__ uint64_t tau_s;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const float* row = distmat + q * ld;
-  const bool masked = q_pids != nullptr;
-  const int64_t qp = masked ? q_pids[q] : 0, qc = masked ? q_camids[q] : 0;
-  if (tid == 0) { count = 0; tau_s = kPadKey; }
-  __syncthreads();
-  constexpr int kTile = kTopkThreads * 4;
-  for (int64_t g0 = 0; g0 < G; g0 += kTile) {
-    const uint64_t tau = tau_s;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t g = g0 + j * kTopkThreads + tid;
-      if (g < G) {
-        const uint64_t pe = pack_key(__ldcs(row + g), (uint32_t)(g + g_offset));
-        if (pe < tau) {
-          const bool is_junk = masked && g_pids[g] == qp && g_camids[g] == qc;   // rank.py:136
-          if (!is_junk) cand[atomicAdd(&count, 1)] = pe;
-        }
-      }
-    }
+  TopkArgs a;
+  a.row = distmat + q * ld;
+  a.G = G;
+  a.g_offset = g_offset;
+  a.masked = q_pids != nullptr;
+  a.qp = a.masked ? q_pids[q] : 0;
+  a.qc = a.masked ? q_camids[q] : 0;
+  a.g_pids = g_pids;
+  a.g_camids = g_camids;
+  a.k = k;
+  int n = -1;
+  if (k <= kTopkFastMaxK && G >= 4 * kTopkThreads) n = topk_select_path(a, cand, &count);
+  if (n < 0) {
     __syncthreads();
-    const int filled = count;                // snapshot taken between two barriers: every thread sees the same value
-    __syncthreads();                         // (without it fast threads would already be appending the next tile)
-    if (filled > kTopkBuf - kTile) {         // next tile could overflow: keep the k best, tighten the threshold
-      const int n = filled;
-      for (int i = n + tid; i < kTopkBuf; i += kTopkThreads) cand[i] = kPadKey;
-      block_bitonic_sort(cand, kTopkBuf);
-      if (tid == 0) { count = min(n, k); if (n >= k) tau_s = cand[k - 1]; }
-      __syncthreads();
-    }
+    n = topk_stream_path(a, cand, &count, &tau_s);
   }
-  const int n = count;
   const int np = next_pow2(max(n, 2));
   for (int i = n + tid; i < np; i += kTopkThreads) cand[i] = kPadKey;
   block_bitonic_sort(cand, np);
@@ -831,7 +903,7 @@ topk_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
     if (i < n) {
       const uint32_t gi = (uint32_t)cand[i];
       idx_out[q * k + i] = (int32_t)gi;
-      val_out[q * k + i] = row[(int64_t)gi - g_offset];
+      val_out[q * k + i] = a.row[(int64_t)gi - g_offset];
     } else {
       idx_out[q * k + i] = -1;
       val_out[q * k + i] = __int_as_float(0x7f800000);
