@@ -269,16 +269,29 @@ def run_ours(args):
     gemm_tflops = flops / (stage_ms["distmat_f16x3"] * 1e-3) / 1e12
     gemm1_tflops = flops / (stage_ms["distmat_bf16_1pass"] * 1e-3) / 1e12
     count_gbs = 4.0 * Q * Gs / (stage_ms["rank_count"] * 1e-3) / 1e9
-    roofline = {"kernel": "distmat_umma_kernel (f16x3: 3 tcgen05 passes per k block)", "bound": "tensor",
-                "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None,
-                "peak_source": peaks["source"] + " (burst)",
-                "note": "achieved counts ALGORITHMIC flops 2*Q*G*D once; the fp32-equivalent split issues 3x that on the tensor pipe"}
+    traffic, traffic_1p, traffic_cnt = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.isfile(tpath) and n_gpus == 1:          # ncu capture of the same single-GPU shapes (bytes per launch)
+        tj = json.load(open(tpath))
+        traffic = tj["distmat_umma_chunked_kernel"]["dram_read_bytes"] + tj["distmat_umma_chunked_kernel"]["dram_write_bytes"]
+        traffic_1p = tj["distmat_umma_kernel_bf16_1pass"]["dram_read_bytes"] + tj["distmat_umma_kernel_bf16_1pass"]["dram_write_bytes"]
+        traffic_cnt = tj["rank_count_warp_kernel"]["dram_read_bytes"] + tj["rank_count_warp_kernel"]["dram_write_bytes"]
+    roofline = {"kernel": "distmat_umma_chunked_kernel (f16x3: fp16 hi/lo split, 3 tcgen05 passes per k block, chunked accumulation)",
+                "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic,
+                "peak_source": peaks["source"] + " (burst: the kernel is timed alone)",
+                "issued_tflops": 3 * gemm_tflops, "issued_frac": 3 * gemm_tflops / peaks["bf16_tflops"],
+                "algorithmic_flops_per_launch": flops,
+                "note": "achieved counts ALGORITHMIC flops 2*Q*G*D once; the fp32-grade split issues 3x that on the tensor "
+                        "pipe (issued_*). traffic = DRAM bytes per launch from profiles/r1_ncu_full_summary.txt"}
     extra = {
-        "roofline_bf16_1pass": {"bound": "tensor", "achieved": gemm1_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                                "frac": gemm1_tflops / peaks["bf16_tflops"]},
-        "roofline_rank_count": {"bound": "hbm", "achieved": count_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": count_gbs / peaks["hbm_gbs"], "algorithmic_bytes": 4 * Q * Gs},
+        "roofline_bf16_1pass": {"kernel": "distmat_umma_kernel<1> (one tcgen05 pass on bf16-rounded features; not parity grade "
+                                          "for f32 inputs, exact for bf16 inputs)", "bound": "tensor", "achieved": gemm1_tflops,
+                                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm1_tflops / peaks["bf16_tflops"],
+                                "traffic": traffic_1p},
+        "roofline_rank_count": {"kernel": "rank_count_warp_kernel", "bound": "hbm", "achieved": count_gbs, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": count_gbs / peaks["hbm_gbs"], "algorithmic_bytes": 4 * Q * Gs,
+                                "traffic": traffic_cnt},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
     }
 
