@@ -63,3 +63,45 @@ def test_no_cpu_fallback():
         compute_distance_matrix(torch.rand(4, 8), torch.rand(5, 8), "manhattan")
     with pytest.raises(AssertionError):
         compute_distance_matrix(torch.rand(4, 8), torch.rand(5, 9))
+
+
+def test_patch_torchreid_rebinds_the_three_call_sites(monkeypatch):
+    """ieee_b200.patch_torchreid(): the names the fork's engine imported (engine.py:18-19, utils/__init__.py:4)."""
+    import sys
+    import types
+
+    import ieee_b200
+    from ieee_b200.metrics import distance, rank
+    from ieee_b200.utils import rerank
+
+    fake_engine = types.ModuleType("torchreid.engine.engine")
+    fake_engine.compute_distance_matrix = fake_engine.evaluate_rank = fake_engine.re_ranking = object()
+    fake_utils = types.ModuleType("torchreid.utils")
+    fake_utils.re_ranking = object()
+    monkeypatch.setitem(sys.modules, "torchreid", types.ModuleType("torchreid"))
+    monkeypatch.setitem(sys.modules, "torchreid.engine.engine", fake_engine)
+    monkeypatch.setitem(sys.modules, "torchreid.utils", fake_utils)
+    for name in ("torchreid.metrics.distance", "torchreid.metrics.rank", "torchreid.utils.rerank"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    ieee_b200.patch_torchreid()
+    assert fake_engine.compute_distance_matrix is distance.compute_distance_matrix
+    assert fake_engine.evaluate_rank is rank.evaluate_rank
+    assert fake_engine.re_ranking is rerank.re_ranking and fake_utils.re_ranking is rerank.re_ranking
+    assert sys.modules["torchreid.metrics.rank"] is rank and sys.modules["torchreid.metrics.distance"] is distance
+
+
+def test_signatures_match_the_reference():
+    """Same parameter names and defaults as distance.py:6, rank.py:246-255 and rerank.py:31."""
+    import inspect
+
+    from ieee_b200.metrics import compute_distance_matrix, evaluate_rank
+    from ieee_b200.utils import re_ranking
+
+    p = inspect.signature(compute_distance_matrix).parameters
+    assert list(p)[:3] == ["input1", "input2", "metric"] and p["metric"].default == "euclidean"
+    p = inspect.signature(evaluate_rank).parameters
+    assert list(p) == ["distmat", "q_pids", "g_pids", "q_camids", "g_camids", "max_rank", "use_metric_cuhk03", "use_cython"]
+    assert (p["max_rank"].default, p["use_metric_cuhk03"].default, p["use_cython"].default) == (20, False, True)
+    p = inspect.signature(re_ranking).parameters
+    assert list(p) == ["q_g_dist", "q_q_dist", "g_g_dist", "k1", "k2", "lambda_value"]
+    assert (p["k1"].default, p["k2"].default, p["lambda_value"].default) == (20, 6, 0.3)
