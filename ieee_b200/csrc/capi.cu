@@ -67,11 +67,11 @@ int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, con
            int64_t G, int32_t k1, int32_t k2, double lambda_value, float* out, int64_t ldo, void* workspace,
            size_t workspace_bytes, cudaStream_t stream);
 
-static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default (1) pairing of the tensor-core kernel
+static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default (2) pairing of the tensor-core kernel
 static int cta_group_default() {
   if (g_cta_group < 0) {
     const char* e = getenv("IEEE_B200_CTA_GROUP");
-    g_cta_group = (e && e[0] == '2') ? 2 : 1;
+    g_cta_group = (e && e[0] == '1') ? 1 : 2;
   }
   return g_cta_group;
 }

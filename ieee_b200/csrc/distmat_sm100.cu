@@ -290,10 +290,12 @@ constexpr int kEpiWarpsC = 8;
 constexpr int kThreadsC = 128 + 32 * kEpiWarpsC;
 constexpr int kPitchC = 17;                      // floats; padded 32 x 16 transpose tile (fallback store path)
 
+template <int CG>
 struct GemmCfgC {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = (CG == 1) ? 4 : 6;
+  static constexpr int kBRows = BLOCK_N / CG;
   static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kEpiTileBytes = 2560;   // 32 x 16 fp32 (2 KB, SWIZZLE_64B) / 32 x 17 padded (2176 B)
   static constexpr uint32_t kEpiColBytes = 2 * 128 * 4;
@@ -305,11 +307,12 @@ struct GemmCfgC {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
+template <int CG>
 __global__ void __launch_bounds__(kThreadsC, 1)
 distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                             const __grid_constant__ CUtensorMap tm_out, const GemmParams p, const int chunk_kb) {
-  using Cfg = GemmCfgC;
+  using Cfg = GemmCfgC<CG>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -317,14 +320,16 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tmem_full_bar = bars + 2 * kStages;
-  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint64_t* full_bar = bars;                          // lives in the pair leader for CG == 2
+  uint64_t* empty_bar = bars + kStages;               // per CTA
+  uint64_t* tmem_full_bar = bars + 2 * kStages;       // per CTA
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // leader
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
+  const bool is_leader = cta_rank == 0;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_a_hi);
@@ -337,22 +342,24 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CG);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarpsC * 32);
+      mbar_init(&tmem_empty_bar[i], CG * kEpiWarpsC * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_ptr_smem, 512);
+  if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, 512);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int group_id = blockIdx.x / CG;
+  const int num_groups = gridDim.x / CG;
   const int num_chunks = (p.num_kb + chunk_kb - 1) / chunk_kb;
 
   if (warp < 4) {
@@ -362,45 +369,57 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
         int stage = 0;
         uint32_t phase = 0;
         const int total_kb = p.num_kb * p.nseg;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = group_id; t < num_tiles; t += num_groups) {
           const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+          const int row_a = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+          const int row_b = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
           for (int kb = 0; kb < total_kb; ++kb) {
             const int kk = kb / p.nseg, seg = kb - kk * p.nseg;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d((seg == 2) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], smem_a + stage * Cfg::kABytes, kk * BLOCK_K,
-                        m_blk * BLOCK_M);
-            tma_load_2d((seg == 1) ? &tm_b_lo : &tm_b_hi, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kk * BLOCK_K,
-                        n_blk * BLOCK_N);
+            const CUtensorMap* ma = (seg == 2) ? &tm_a_lo : &tm_a_hi;
+            const CUtensorMap* mb = (seg == 1) ? &tm_b_lo : &tm_b_hi;
+            void* sa = smem_a + stage * Cfg::kABytes;
+            void* sb = smem_b + stage * Cfg::kBBytes;
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_2d(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+              tma_load_2d(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+            } else {
+              if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              tma_load_2d_pair(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+              tma_load_2d_pair(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+              if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (elect_one()) {
+      // ===================== MMA issuer (pair leader only) =====================
+      if (is_leader && elect_one()) {
         const uint32_t idesc = p.idesc;
         int stage = 0;
         uint32_t phase = 0;
         int ci = 0;   // chunk counter over the whole kernel: TMEM stage = ci & 1
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = group_id; t < num_tiles; t += num_groups) {
           for (int c = 0; c < num_chunks; ++c, ++ci) {
             const int acc = ci & 1;
             mbar_wait(&tmem_empty_bar[acc], ((ci >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            const int kb_begin = c * chunk_kb * p.nseg;
             const int kb_end = min(p.num_kb, (c + 1) * chunk_kb) * p.nseg;
-            for (int kb = c * chunk_kb * p.nseg; kb < kb_end; ++kb) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
               const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
               const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_bf16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != c * chunk_kb * p.nseg) || k != 0);
-              umma_commit<1>(&empty_bar[stage]);
-              if (kb == kb_end - 1) umma_commit<1>(&tmem_full_bar[acc]);
+                umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != kb_begin) || k != 0);
+              umma_commit<CG>(&empty_bar[stage]);
+              if (kb == kb_end - 1) umma_commit<CG>(&tmem_full_bar[acc]);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -418,9 +437,9 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
     float* col_rg = reinterpret_cast<float*>(my_epi + Cfg::kEpiTileBytes);   // [128]
     float* col_sg = col_rg + 128;                                            // [128]
     int ci = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = group_id; t < num_tiles; t += num_groups) {
       const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
-      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int col0 = n_blk * BLOCK_N + half * 128;
       const int my_row = row0 + lane;
       const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : 1.0f;
@@ -453,7 +472,7 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
       }
       if (row0 >= p.Q || (p.debug & 1)) continue;
       // d = fma(coef * sg, sum, rq + rg), 16 columns at a time
@@ -461,18 +480,20 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
       for (int s16 = 0; s16 < 8; ++s16) {
         const int cbase = col0 + s16 * 16;
         if (cbase >= p.G) break;                 // warp-uniform
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          o[i] = __fmaf_rn(coef_row * col_sg[s16 * 16 + i], r[s16 * 16 + i], __fadd_rn(rq_row, col_rg[s16 * 16 + i]));
+        auto out4 = [&](int k) {                 // outputs 4k .. 4k+3 of this 16-column group
+          const int i = s16 * 16 + 4 * k;
+          return make_float4(__fmaf_rn(coef_row * col_sg[i], r[i], __fadd_rn(rq_row, col_rg[i])),
+                             __fmaf_rn(coef_row * col_sg[i + 1], r[i + 1], __fadd_rn(rq_row, col_rg[i + 1])),
+                             __fmaf_rn(coef_row * col_sg[i + 2], r[i + 2], __fadd_rn(rq_row, col_rg[i + 2])),
+                             __fmaf_rn(coef_row * col_sg[i + 3], r[i + 3], __fadd_rn(rq_row, col_rg[i + 3])));
+        };
         if (p.tma_store) {
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           // 32 rows x 64 bytes, SWIZZLE_64B: 16-byte chunk k of row r lives at chunk k ^ ((r >> 1) & 3)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tile) + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
-                make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tile) + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = out4(k);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -482,7 +503,13 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
         } else {
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) tile[lane * kPitchC + i] = o[i];
+          for (int k = 0; k < 4; ++k) {
+            const float4 o = out4(k);
+            tile[lane * kPitchC + 4 * k] = o.x;
+            tile[lane * kPitchC + 4 * k + 1] = o.y;
+            tile[lane * kPitchC + 4 * k + 2] = o.z;
+            tile[lane * kPitchC + 4 * k + 3] = o.w;
+          }
           __syncwarp();
           const int cl = lane & 15, rh = lane >> 4;          // 2 rows x 16 columns per instruction
 #pragma unroll 4
@@ -498,8 +525,8 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -610,9 +637,10 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   return IEEE_OK;
 }
 
+template <int CG>
 static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
                                int precision, float* out, int64_t ldo, cudaStream_t stream, int chunk_kb) {
-  using Cfg = GemmCfgC;
+  using Cfg = GemmCfgC<CG>;
   PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
   const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
   const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
@@ -620,10 +648,10 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
   int rc;
   if ((rc = make_tmap(&ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, BLOCK_N, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
   if (precision == IEEE_PREC_F16X3) {
     if ((rc = make_tmap(&ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, BLOCK_N, BLOCK_K))) return rc;
+    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
@@ -641,9 +669,9 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
   p.G = (int)G;
   p.num_kb = (int)(lq.Dp / BLOCK_K);
   p.nseg = precision == IEEE_PREC_F16X3 ? 3 : 1;
-  p.num_m_tiles = (int)((Q + BLOCK_M - 1) / BLOCK_M);
+  p.num_m_tiles = (int)((Q + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
-  p.idesc = umma_idesc_16bit(BLOCK_M, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
+  p.idesc = umma_idesc_16bit(BLOCK_M * CG, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
   p.debug = g_debug_flags;
   p.tma_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 && !(g_debug_flags & 4)) ? 1 : 0;
   if (p.tma_store) {
@@ -652,25 +680,39 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
     t_out = ta_hi;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
+  int groups = sm_count() / CG;
+  if (groups > num_tiles) groups = num_tiles;
   static bool attr_set = false;
   if (!attr_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_chunked_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmemBytes));
     attr_set = true;
   }
-  distmat_umma_chunked_kernel<<<grid, kThreadsC, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, t_out, p, chunk_kb);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(kThreadsC);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_chunked_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, t_out, p, chunk_kb));
   count_launch();
-  IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
 
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
                  float* out, int64_t ldo, cudaStream_t stream, int cta_group) {
   // chunked accumulation serves the fp32-grade mode; the 1-pass BF16 mode keeps the whole K in TMEM (throughput mode)
-  if (cta_group == 1 && g_accum_chunk_kb > 0 && (precision == IEEE_PREC_F16X3 || (g_debug_flags & 8)))
-    return launch_umma_chunked(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
+  if (g_accum_chunk_kb > 0 && (precision == IEEE_PREC_F16X3 || (g_debug_flags & 8))) {
+    if (cta_group == 2)
+      return launch_umma_chunked<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
+    return launch_umma_chunked<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
+  }
   if (cta_group == 2)
     return launch_umma<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);
   return launch_umma<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);

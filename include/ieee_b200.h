@@ -64,10 +64,10 @@ const char* ieee_last_error(void);
 int ieee_abi_version(void);
 /* Number of SMs / compute capability (major*10+minor) of the current device; IEEE_ERR_CUDA without one. */
 int ieee_device_info(int* sm_count, int* compute_capability);
-/* Tensor-core kernel pairing: 1 (default) = tcgen05 cta_group::1, one 128 x 256 tile per SM;
- * 2 = cta_group::2, one 256 x 256 tile per SM pair.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
+/* Tensor-core kernel pairing: 2 (default) = tcgen05 cta_group::2, one 256 x 256 tile per SM pair;
+ * 1 = cta_group::1, one 128 x 256 tile per SM.  Returns the previous value.  (Env: IEEE_B200_CTA_GROUP.) */
 int ieee_set_cta_group(int cta_group);
-/* Accumulation chunking of the tensor-core contraction (cta_group 1): the tcgen05 fp32 accumulator truncates, so
+/* Accumulation chunking of the tensor-core contraction: the tcgen05 fp32 accumulator truncates, so
  * every `k_slices` 64-wide K-slices the partial sums are moved to registers and added there with round-to-nearest.
  * 0 = accumulate the whole K in TMEM (fastest, ~1e-5 relative bias on the dot product); default 4 (F16X3 mode;
  * the 1-pass BF16 mode always accumulates the whole K in TMEM).

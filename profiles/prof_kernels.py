@@ -50,18 +50,18 @@ def main():
     out = torch.empty((Q, pitch), dtype=torch.float32, device=dev)[:, :G]     # 128-byte row pitch -> TMA-store epilogue
     res = {}
     packs = {p: (PackedFeatures(qf, "euclidean", False, p), PackedFeatures(gf, "euclidean", False, p)) for p in ("bf16", "f16x3")}
-    configs = [(cg, dbg) for cg in (1, 2) for dbg in ((0, 1, 4) if args.sweep else (0,))]
+    configs = [(cg, dbg) for cg in (2, 1) for dbg in ((0, 1, 4) if args.sweep else (0,))]
     for cg, dbg in configs:
         lib.ieee_set_cta_group(cg)
         lib.ieee_set_debug_flags(dbg)
-        for chunk in ((0, 1, 2, 4, 9) if cg == 1 and dbg == 0 else (0,)):
+        for chunk in ((0, 2, 4, 9) if dbg == 0 else (0,)):
             lib.ieee_set_accum_chunk(chunk)
             for prec in ("bf16", "f16x3"):
                 q, g = packs[prec]
                 tmin, tavg = timeit(lambda: packed_distmat(q, g, out), args.reps, flush)
                 res[f"distmat_{prec}_cg{cg}_dbg{dbg}_chunk{chunk}"] = {"ms_min": tmin, "ms_avg": tavg, "tflops_alg": flops / tmin / 1e9}
     lib.ieee_set_accum_chunk(4)
-    lib.ieee_set_cta_group(1)
+    lib.ieee_set_cta_group(2)
     lib.ieee_set_debug_flags(0)
     q, g = packs["f16x3"]
     packed_distmat(q, g, out)
