@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   if (n_norm > 0 || mode == PACK_F16_HILO) {
     for (int pass = 0; pass < (n_norm > 0 ? n_norm : 1); ++pass) {
       float s = 0.f;
+#pragma unroll 6
       for (int i = lane * VEC; i < D; i += 32 * VEC) {
         float v[VEC];
         RowLoader<T, VEC>::load(xr, i, v);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   }
   const float down = ldexpf(1.0f, -e);   // exact power of two
   float sq = 0.f;
+#pragma unroll 6
   for (int i = lane * VEC; i < Dp; i += 32 * VEC) {
     float v[VEC];
     if (i < D) {

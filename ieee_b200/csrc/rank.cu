@@ -225,7 +225,7 @@ __host__ __device__ inline CountSmemPlan count_smem_plan(int Rp) {
   CountSmemPlan p;
   p.hist_off = size_t(Rp) * 8;                          // after T[Rp] u64
   p.cell_off = p.hist_off + size_t(Rp + 2) * 4;         // hist[Rp + 2] i32
-  p.misc_off = p.cell_off + size_t(kLutCells) * 4;      // cell[L] u32
+  p.misc_off = p.cell_off + size_t(kLutCells + 2) * 4;  // cell[L + 2] u32 (guard cells at both ends)
   p.priv_off = (p.misc_off + 64 * 4 + 15) & ~size_t(15);
   const int want = Rp + 2;
   p.priv_bins = want * kCountThreads * 4 <= kPrivateBinBudget ? want : kPrivateBinBudget / (kCountThreads * 4);
@@ -266,31 +266,56 @@ __device__ __forceinline__ int exact_bin(CountCtx& c, int lo, int n, uint64_t pe
 // element increments exactly one counter -- bin 0 if it precedes all thresholds, the trash bin R + 1 if it follows
 // them (or is NaN), else its bin from the cell table; only cells that hold a threshold take a (reconverging) branch.
 template <int MODE, int NT>
-__device__ __forceinline__ void count_visit(CountCtx& c, float d, uint32_t g) {
-  int b;
-  if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
-    // thresholds are finite here, so float compares order exactly like the keys (NaN fails d <= hi: ranks last)
-    const bool in = d <= c.hi;
-    const bool before = d < c.lo;
-    const uint32_t ce = c.cell[(int)((d - c.lo) * c.scale) & (kLutCells - 1)];   // garbage-safe: masked, then overridden
-    b = (int)(ce & 0xFFFFFu);
-    if (in && !before && (ce >> 20)) b = exact_bin(c, b, (int)(ce >> 20), pack_key(d, g + c.g_offset));
-    b = before ? 0 : b;
-    b = in ? b : c.trash;
-  } else {
-    const uint32_t ke = order_key(d);
-    const uint64_t pe = (uint64_t(ke) << 32) | (g + c.g_offset);
-    int a = 0, e = c.R;
-    while (a < e) { const int m = (a + e) >> 1; if (c.T[m] < pe) a = m + 1; else e = m; }
-    int same = 0;
-    bool is_thr = false;
-    for (int j = a; j < c.R && (uint32_t)(c.T[j] >> 32) == ke; ++j) { same++; is_thr |= (c.T[j] == pe); }
-    for (int j = a - 1; j >= 0 && (uint32_t)(c.T[j] >> 32) == ke; --j) same++;
-    if (!is_thr) c.ties += same;
-    b = (ke > c.kmax) ? c.trash : a;
+__device__ __forceinline__ void count_bump(CountCtx& c, int b, int delta) {
+  if constexpr (MODE == COUNT_LUT_PRIVATE) c.priv[b * NT] += delta;
+  else atomicAdd(&c.hist[b], delta);
+}
+
+// Cell of a distance in the guarded table: index 0 = "before every threshold" (bin 0), 1 .. L = the L cells over
+// [lo, hi], L + 1 = "after every threshold" (trash bin).  floor() sends d < lo below 0 and d >> hi beyond L; NaN
+// converts to 0 and lands in cell 1, which holds T_0 and therefore takes the exact path (key order: last).
+__device__ __forceinline__ uint32_t count_cell(const CountCtx& c, float d) {
+  int ci = __float2int_rd((d - c.lo) * c.scale);
+  ci = max(min(ci, kLutCells) + 1, 0);
+  return c.cell[ci];
+}
+
+// Branch-free per-element body (the lanes of a warp stay converged and the 16 elements in flight interleave): every
+// element increments exactly one counter, tentatively the FIRST bin of its cell; the return value says whether the
+// cell holds thresholds, in which case count_fix() later moves the count to the exact bin.
+template <int MODE, int NT>
+__device__ __forceinline__ uint32_t count_visit(CountCtx& c, float d) {
+  const uint32_t ce = count_cell(c, d);
+  count_bump<MODE, NT>(c, (int)(ce & 0xFFFFFu), 1);
+  return (ce >> 20) ? 1u : 0u;
+}
+
+// Exact (key, index) placement of an element whose cell holds thresholds (rare).  Must stay inlined: a real call
+// would force the context struct into local memory and turn every c.lo / c.scale / c.priv access into a local load.
+template <int MODE, int NT>
+__device__ __forceinline__ void count_fix(CountCtx& c, float d, uint32_t g) {
+  const uint32_t ce = count_cell(c, d);
+  const int tent = (int)(ce & 0xFFFFFu);
+  const int b = exact_bin(c, tent, (int)(ce >> 20), pack_key(d, g + c.g_offset));
+  if (b != tent) {
+    count_bump<MODE, NT>(c, tent, -1);
+    count_bump<MODE, NT>(c, b, 1);
   }
-  if constexpr (MODE == COUNT_LUT_PRIVATE) c.priv[b * NT] += 1;
-  else atomicAdd(&c.hist[b], 1);
+}
+
+// Generic path (non-finite / degenerate thresholds): binary search over all of T, shared atomics.
+template <int NT>
+__device__ __forceinline__ void count_visit_search(CountCtx& c, float d, uint32_t g) {
+  const uint32_t ke = order_key(d);
+  const uint64_t pe = (uint64_t(ke) << 32) | (g + c.g_offset);
+  int a = 0, e = c.R;
+  while (a < e) { const int m = (a + e) >> 1; if (c.T[m] < pe) a = m + 1; else e = m; }
+  int same = 0;
+  bool is_thr = false;
+  for (int j = a; j < c.R && (uint32_t)(c.T[j] >> 32) == ke; ++j) { same++; is_thr |= (c.T[j] == pe); }
+  for (int j = a - 1; j >= 0 && (uint32_t)(c.T[j] >> 32) == ke; --j) same++;
+  if (!is_thr) c.ties += same;
+  atomicAdd(&c.hist[(ke > c.kmax) ? c.trash : a], 1);
 }
 
 // NT threads (a CTA or one warp) stream one row; `tid` is the thread's index among them.
@@ -299,29 +324,34 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
   const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
   int head = (int)(((16 - (addr & 15)) & 15) >> 2);
   if (head > G) head = G;
-  for (int g = tid; g < head; g += NT) count_visit<MODE, NT>(c, row[g], (uint32_t)g);
   const int nvec = (G - head) >> 2;
   const float4* rv = reinterpret_cast<const float4*>(row + head);
-  int i = tid;
-  if constexpr (MODE != COUNT_SEARCH_ATOMIC) {
+  if constexpr (MODE == COUNT_SEARCH_ATOMIC) {
+    for (int g = tid; g < G; g += NT) count_visit_search<NT>(c, row[g], (uint32_t)g);
+    return;
+  } else {
+    auto one = [&](float d, uint32_t g) { if (count_visit<MODE, NT>(c, d)) count_fix<MODE, NT>(c, d, g); };
+    for (int g = tid; g < head; g += NT) one(row[g], (uint32_t)g);
+    int i = tid;
     for (; i + 3 * NT < nvec; i += 4 * NT) {   // 4 independent 16-byte loads in flight
+      // (a register double-buffer that keeps the next batch in flight was measured slower: occupancy)
       const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + NT), a2 = __ldcs(rv + i + 2 * NT), a3 = __ldcs(rv + i + 3 * NT);
       uint32_t g0 = (uint32_t)(head + 4 * i);
-      count_visit<MODE, NT>(c, a0.x, g0); count_visit<MODE, NT>(c, a0.y, g0 + 1); count_visit<MODE, NT>(c, a0.z, g0 + 2); count_visit<MODE, NT>(c, a0.w, g0 + 3);
+      one(a0.x, g0); one(a0.y, g0 + 1); one(a0.z, g0 + 2); one(a0.w, g0 + 3);
       g0 += 4 * NT;
-      count_visit<MODE, NT>(c, a1.x, g0); count_visit<MODE, NT>(c, a1.y, g0 + 1); count_visit<MODE, NT>(c, a1.z, g0 + 2); count_visit<MODE, NT>(c, a1.w, g0 + 3);
+      one(a1.x, g0); one(a1.y, g0 + 1); one(a1.z, g0 + 2); one(a1.w, g0 + 3);
       g0 += 4 * NT;
-      count_visit<MODE, NT>(c, a2.x, g0); count_visit<MODE, NT>(c, a2.y, g0 + 1); count_visit<MODE, NT>(c, a2.z, g0 + 2); count_visit<MODE, NT>(c, a2.w, g0 + 3);
+      one(a2.x, g0); one(a2.y, g0 + 1); one(a2.z, g0 + 2); one(a2.w, g0 + 3);
       g0 += 4 * NT;
-      count_visit<MODE, NT>(c, a3.x, g0); count_visit<MODE, NT>(c, a3.y, g0 + 1); count_visit<MODE, NT>(c, a3.z, g0 + 2); count_visit<MODE, NT>(c, a3.w, g0 + 3);
+      one(a3.x, g0); one(a3.y, g0 + 1); one(a3.z, g0 + 2); one(a3.w, g0 + 3);
     }
+    for (; i < nvec; i += NT) {
+      const float4 a = __ldcs(rv + i);
+      const uint32_t g0 = (uint32_t)(head + 4 * i);
+      one(a.x, g0); one(a.y, g0 + 1); one(a.z, g0 + 2); one(a.w, g0 + 3);
+    }
+    for (int g = head + 4 * nvec + tid; g < G; g += NT) one(row[g], (uint32_t)g);
   }
-  for (; i < nvec; i += NT) {
-    const float4 a = __ldcs(rv + i);
-    const uint32_t g0 = (uint32_t)(head + 4 * i);
-    count_visit<MODE, NT>(c, a.x, g0); count_visit<MODE, NT>(c, a.y, g0 + 1); count_visit<MODE, NT>(c, a.z, g0 + 2); count_visit<MODE, NT>(c, a.w, g0 + 3);
-  }
-  for (int g = head + 4 * nvec + tid; g < G; g += NT) count_visit<MODE, NT>(c, row[g], (uint32_t)g);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -334,7 +364,7 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
 constexpr int kWarpQ = 8;            // queries (warps) per CTA
 constexpr int kWarpRmax = 64;        // thresholds per query the private table holds
 __host__ __device__ inline int warp_smem_per_query(int rmax) {   // T[rmax] u64 | hist[rmax + 2] | cell[1024] | priv[rmax + 2][32]
-  return ((rmax * 8 + (rmax + 2) * 4 + kLutCells * 4 + (rmax + 2) * 32 * 4) + 15) & ~15;
+  return ((rmax * 8 + (rmax + 2) * 4 + (kLutCells + 2) * 4 + (rmax + 2) * 32 * 4) + 15) & ~15;
 }
 
 __global__ void __launch_bounds__(32 * kWarpQ)
@@ -348,7 +378,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   uint64_t* T = reinterpret_cast<uint64_t*>(mine);                                   // [rmax]
   int32_t* hist = reinterpret_cast<int32_t*>(mine + rmax * 8);                        // [rmax + 2]
   uint32_t* cell = reinterpret_cast<uint32_t*>(hist + rmax + 2);                      // [1024]
-  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells);                       // [rmax + 2][32]
+  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells + 2);                   // [rmax + 2][32]
   const int64_t q = (int64_t)blockIdx.x * kWarpQ + w;
   if (q >= Q) return;
   const int stride = shards * cap + 1;
@@ -373,7 +403,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
     T[pos] = me;
   }
-  for (int i = lane; i < kLutCells; i += 32) cell[i] = 0;
+  for (int i = lane; i < kLutCells + 2; i += 32) cell[i] = 0;
   __syncwarp();
   for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
   for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;     // own column only: i % 32 == lane
@@ -385,12 +415,12 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   if (use_lut) {
     for (int k = lane; k < R; k += 32) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
-      atomicAdd(&cell[(int)((d - lo) * scale) & (kLutCells - 1)], 1u << 20);
+      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), kLutCells - 1)], 1u << 20);
     }
     __syncwarp();
     // exclusive scan over the 1024 cells, 32 at a time (lane <-> cell: conflict-free), carry in a register
     int carry = 0;
-    for (int k0 = 0; k0 < kLutCells; k0 += 32) {
+    for (int k0 = 1; k0 <= kLutCells; k0 += 32) {
       const int cnt = (int)(cell[k0 + lane] >> 20);
       int incl = cnt;
 #pragma unroll
@@ -398,6 +428,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
       cell[k0 + lane] = (uint32_t)(carry + incl - cnt) | ((uint32_t)cnt << 20);
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) { cell[0] = 0; cell[kLutCells + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
   }
   __syncwarp();
   CountCtx c;
@@ -465,7 +496,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
 
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
   if (tid == 0) { misc[0] = 0; misc[1] = 0; }
-  for (int i = tid; i < kLutCells; i += kCountThreads) cell[i] = 0;
+  for (int i = tid; i < kLutCells + 2; i += kCountThreads) cell[i] = 0;
   __syncthreads();
   // unsorted staging: the (not yet live) private-bin area when it is large enough, else T itself
   const bool stage_in_priv = size_t(Rp) * 8 <= size_t(plan.priv_bins) * kCountThreads * 4;
@@ -518,13 +549,13 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   if (use_lut) {
     for (int k = tid; k < R; k += kCountThreads) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
-      atomicAdd(&cell[(int)((d - lo) * scale) & (kLutCells - 1)], 1u << 20);
+      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), kLutCells - 1)], 1u << 20);
     }
     __syncthreads();
     // exclusive scan of the per-cell counts -> first bin of each cell (kLutCells == 4 * kCountThreads)
     int v[4], sum = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { v[j] = (int)(cell[tid * 4 + j] >> 20); sum += v[j]; }
+    for (int j = 0; j < 4; ++j) { v[j] = (int)(cell[1 + tid * 4 + j] >> 20); sum += v[j]; }
     int incl = sum;
     const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -536,9 +567,11 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
     for (int i = 0; i < w; ++i) woff += wsum[i];
     int run = woff + incl - sum;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { cell[tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
+    for (int j = 0; j < 4; ++j) { cell[1 + tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
+    if (tid == 0) { cell[0] = 0; cell[kLutCells + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
   }
   __syncthreads();
+
   // ---- stream the row ---------------------------------------------------------------------------------------
   CountCtx c;
   c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + tid;

@@ -109,8 +109,8 @@ class RetrievalEvaluator:
             # the gallery as packed row chunks [(first row, PackedFeatures)]: one chunk when the features are already
             # in HBM, several when they are streamed from the host (from_host) so that the contraction of chunk i
             # overlaps the PCIe copy of chunk i + 1
+            self.labels = GalleryLabels(g_pids, g_camids, self.device, overlap=True)     # side stream, beside the packing
             self.chunks = [(0, PackedFeatures(gf, dist_metric, normalize_feature, self.precision))] if gf is not None else []
-            self.labels = GalleryLabels(g_pids, g_camids, self.device)
         self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
@@ -125,6 +125,7 @@ class RetrievalEvaluator:
     def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties):
         Qb = dist.shape[0]
         st = RankStages(Qb, cap, self.world, self.device)
+        torch.cuda.current_stream().wait_event(self.labels.ready)
         st.gather(dist, qp, qc, self.labels, self.g_offset)
         if self.world > 1:
             import torch.distributed as dist_

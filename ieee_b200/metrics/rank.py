@@ -43,17 +43,24 @@ def copy_stream(device) -> torch.cuda.Stream:
 class GalleryLabels:
     """Gallery ids on the device plus their pid-sorted grouping (built once, reused per query block)."""
 
-    def __init__(self, g_pids, g_camids, device):
+    def __init__(self, g_pids, g_camids, device, overlap: bool = False):
+        """overlap=True builds the grouping on the side stream (its few tiny kernels then run beside whatever the
+        caller queues next, e.g. the bandwidth-bound feature packing); consumers order themselves after `ready`."""
         self.pids = _as_device(g_pids, torch.int64, device)
         self.camids = _as_device(g_camids, torch.int64, device)
         self.G = self.pids.numel()
         assert self.camids.numel() == self.G
         lib = _lib.load()
         self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
+        self._scratch = torch.empty(64, dtype=torch.int32, device=device)
         with torch.cuda.device(device):
-            _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
-            self._scratch = torch.zeros(64, dtype=torch.int32, device=device)
-            self.ready = torch.cuda.current_stream().record_event()      # grouping queued up to here
+            cur = torch.cuda.current_stream()
+            stream = side_stream(device) if overlap else cur
+            if overlap:
+                stream.wait_stream(cur)                    # label copies / allocations queued so far
+            with torch.cuda.stream(stream):
+                _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
+                self.ready = stream.record_event()         # grouping queued up to here
 
     def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
         """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
