@@ -225,7 +225,8 @@ def run_ours(args):
     # ---- end to end: pinned host buffers in, (cmc, mAP) on the host out ---------------------------------
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
     e2e_value = Q * args.steps / (ms_e2e / 1e3)
-    h2d = qf_host.numel() * 4 + gf_host.numel() * 4 + sum(t.numel() * 8 for t in lab_host)
+    # whole job: every rank copies its gallery shard and 1/N of the queries (all-gathered over NVLink) plus the labels
+    h2d = (Q + G_TOTAL) * DIM * 4 + world * (2 * Q * 8) + 2 * G_TOTAL * 8
     d2h = 4 * MAX_RANK + 64 + 4      # cmc + summary block + the list-capacity int
 
     # ---- per-kernel timing for the roofline (live, CUDA events on the launching stream) -------------------

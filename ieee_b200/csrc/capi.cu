@@ -47,14 +47,14 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
                 uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream);
 size_t rank_count_smem(int shards, int cap);
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
-               const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
+               const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream);
 size_t rank_finalize_workspace_bytes(int64_t Q);
-int rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                        int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, cudaStream_t stream);
 int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
                 const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, cudaStream_t stream);
-int rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                   double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream);
 int topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
@@ -228,20 +228,20 @@ int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, con
 size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap) { return rank_count_smem(shards, cap); }
 
 int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards, int32_t cap,
-                    const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
+                    const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                     int32_t* counts, unsigned long long* ties, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_count(distmat, ld, Q, G, g_offset, shards, cap, rel_all, n_rel_all, junk, n_junk, counts, ties,
+  return rank_count(distmat, ld, Q, G, g_offset, shards, cap, rel_all, n_rel, junk, n_junk, counts, ties,
                     (cudaStream_t)stream);
 }
 
-int ieee_rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+int ieee_rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards,
                             int32_t cap, int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
                             ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_query_metrics(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ap, first, short_list, (cudaStream_t)stream);
+  return rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, short_list, (cudaStream_t)stream);
 }
 
 int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
@@ -253,12 +253,12 @@ int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* shor
 
 size_t ieee_rank_finalize_workspace_bytes(int64_t Q) { return Q > 0 ? rank_finalize_workspace_bytes(Q) : 0; }
 
-int ieee_rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
+int ieee_rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards,
                        int32_t cap, int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                        double* per_query_ap, int32_t* per_query_first, void* workspace, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_finalize(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ties, cmc, summary, per_query_ap,
+  return rank_finalize(counts, Q, G_total, shards, cap, max_rank, ties, cmc, summary, per_query_ap,
                        per_query_first, workspace, (cudaStream_t)stream);
 }
 
@@ -269,9 +269,9 @@ size_t ieee_eval_workspace_bytes(int64_t Q, int64_t G, int32_t cap) {
   size_t b = 0;
   b += align256(gallery_group_bytes(G));
   b += 256;                                        // cap scratch + overflow flag + ties
-  b += 2 * align256(size_t(Q) * cap * 8);          // rel, junk
+  b += 2 * align256(size_t(Q) * (cap + 1) * 8);    // rel (+ embedded count), junk
   b += 2 * align256(size_t(Q) * 4);                // n_rel, n_junk
-  b += align256(size_t(Q) * (cap + 1) * 4);        // counts
+  b += align256(size_t(Q) * (cap + 2) * 4);        // counts
   b += align256(rank_finalize_workspace_bytes(Q));
   return b + 256;
 }
@@ -301,11 +301,11 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
     return IEEE_ERR_CAPACITY;
   }
   cap = need;   // tight lists: less shared memory in the count kernel
-  uint64_t* rel = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
+  uint64_t* rel = static_cast<uint64_t*>(a.take(size_t(Q) * (cap + 1) * 8));
   uint64_t* junk = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
   int32_t* n_rel = static_cast<int32_t*>(a.take(size_t(Q) * 4));
   int32_t* n_junk = static_cast<int32_t*>(a.take(size_t(Q) * 4));
-  int32_t* counts = static_cast<int32_t*>(a.take(size_t(Q) * (cap + 1) * 4));
+  int32_t* counts = static_cast<int32_t*>(a.take(size_t(Q) * (cap + 2) * 4));
   void* fws = a.take(rank_finalize_workspace_bytes(Q));
   if (!rel || !junk || !n_rel || !n_junk || !counts || !fws) {
     set_error("eval: workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
@@ -316,7 +316,7 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
-  return rank_finalize(counts, n_rel, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
+  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
 }
 
 int ieee_topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,

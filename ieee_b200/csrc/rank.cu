@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
     }
     const unsigned mr = __ballot_sync(0xffffffffu, is_rel), mj = __ballot_sync(0xffffffffu, is_junk);
     const unsigned below = (1u << lane) - 1;
-    if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) rel[q * cap + s] = key; }
+    if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) rel[q * (cap + 1) + s] = key; }
     if (is_junk) { const int s = nj + __popc(mj & below); if (s < cap) junk[q * cap + s] = key; }
     nr += __popc(mr);
     nj += __popc(mj);
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
   if (lane == 0) {
     if (nr > cap || nj > cap) { atomicMax(overflow, max(nr, nj)); nr = min(nr, cap); nj = min(nj, cap); }
     n_rel[q] = nr;
+    rel[q * (cap + 1) + cap] = (uint64_t)nr;      // the list carries its own length: one all-gather moves both
     n_junk[q] = nj;
   }
 }
@@ -369,7 +370,7 @@ __host__ __device__ inline int warp_smem_per_query(int rmax) {   // T[rmax] u64 
 
 __global__ void __launch_bounds__(32 * kWarpQ)
 rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
-                       int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
+                       int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                        const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                        unsigned long long* __restrict__ ties_out) {
   extern __shared__ __align__(16) uint8_t ws_raw[];
@@ -381,19 +382,19 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells + 2);                   // [rmax + 2][32]
   const int64_t q = (int64_t)blockIdx.x * kWarpQ + w;
   if (q >= Q) return;
-  const int stride = shards * cap + 1;
+  const int stride = shards * cap + 2;
   int32_t* out = counts + q * stride;
   const int nj = n_junk[q];
   // thresholds of all shards, staged in `priv` (not live yet)
   uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
   int R = 0;
   for (int s = 0; s < shards; ++s) {
-    const int n = n_rel_all[(int64_t)s * Q + q];
-    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * cap;
+    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
+    const int n = (int)src[cap];
     for (int i = lane; i < n; i += 32) Tin[R + i] = src[i];
     R += n;
   }
-  if (lane == 0) out[stride - 1] = nj;
+  if (lane == 0) { out[stride - 1] = nj; out[stride - 2] = n_rel[q]; }
   if (R == 0) return;                       // invalid query (rank.py:142-144)
   __syncwarp();
   // rank sort (keys are distinct)
@@ -479,7 +480,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
 
 __global__ void __launch_bounds__(kCountThreads, 6)
 rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
-                  int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel_all,
+                  int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                   const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                   unsigned long long* __restrict__ ties_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
@@ -491,7 +492,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   int32_t* priv = reinterpret_cast<int32_t*>(cs_raw + plan.priv_off);    // [bins][kCountThreads]
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int stride = shards * cap + 1;
+  const int stride = shards * cap + 2;
   int32_t* out = counts + q * stride;
 
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
@@ -502,8 +503,8 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   const bool stage_in_priv = size_t(Rp) * 8 <= size_t(plan.priv_bins) * kCountThreads * 4;
   uint64_t* Tin = stage_in_priv ? reinterpret_cast<uint64_t*>(priv) : T;
   for (int s = 0; s < shards; ++s) {
-    const int n = n_rel_all[(int64_t)s * Q + q];
-    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * cap;
+    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
+    const int n = (int)src[cap];
     __shared__ int base_s;
     if (tid == 0) { base_s = misc[0]; misc[0] += n; }
     __syncthreads();
@@ -512,7 +513,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   }
   const int R = misc[0];
   const int nj = n_junk[q];
-  if (tid == 0) out[stride - 1] = nj;
+  if (tid == 0) { out[stride - 1] = nj; out[stride - 2] = n_rel[q]; }
   if (R == 0) return;   // invalid query (rank.py:142-144): nothing to rank against
   if (stage_in_priv && R <= 512) {
     // rank sort: keys are distinct (distinct gallery indices), so #smaller is each key's final position
@@ -640,9 +641,9 @@ int g_count_warp_max_g = 65536;   // rows up to this length use the warp-per-que
 size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(max(shards * cap, 2))).total; }
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
-               const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk, const int32_t* n_junk,
+               const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream) {
-  IEEE_REQUIRE(distmat && rel_all && n_rel_all && junk && n_junk && counts, "rank_count: null pointer");
+  IEEE_REQUIRE(distmat && rel_all && n_rel && junk && n_junk && counts, "rank_count: null pointer");
   IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
   if (G <= g_count_warp_max_g && shards * cap <= kWarpRmax && !(g_debug_flags & 16)) {     // short rows: one warp per query
@@ -654,7 +655,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
       wattr = wsmem;
     }
     rank_count_warp_kernel<<<(unsigned)((Q + kWarpQ - 1) / kWarpQ), 32 * kWarpQ, wsmem, stream>>>(
-        distmat, ld, Q, (int)G, g_offset, shards, cap, rmax, rel_all, n_rel_all, junk, n_junk, counts, ties);
+        distmat, ld, Q, (int)G, g_offset, shards, cap, rmax, rel_all, n_rel, junk, n_junk, counts, ties);
     count_launch();
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
@@ -669,7 +670,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
     smem_set = smem;
   }
   rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, Rp, rel_all,
-                                                                  n_rel_all, junk, n_junk, counts, ties);
+                                                                  n_rel, junk, n_junk, counts, ties);
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -695,16 +696,15 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
 // ---------------------------------------------------------------------------------------------------------
 // finalize: per-query AP / first hit, then one deterministic CTA-wide reduction.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ n_rel_all,
+__global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restrict__ counts,
                                                           int64_t Q, int64_t G_total, int shards, int cap, int max_rank,
                                                           double* __restrict__ ap, int32_t* __restrict__ first,
                                                           int32_t* __restrict__ is_short) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  int R = 0;
-  for (int s = 0; s < shards; ++s) R += n_rel_all[(int64_t)s * Q + q];
-  const int stride = shards * cap + 1;
+  const int stride = shards * cap + 2;
   const int32_t* c = counts + q * stride;
+  const int R = c[stride - 2];            // relevant items over all shards (summed with the counts)
   if (R == 0) { ap[q] = 0.0; first[q] = -1; is_short[q] = 0; return; }
   // rank.py:155-160: AP = (1/R) sum_k (k+1) / (pos_k + 1), float64
   double s = 0.0;
@@ -776,12 +776,12 @@ __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restr
 
 size_t rank_finalize_workspace_bytes(int64_t Q) { return align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4); }
 
-int rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                        int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, cudaStream_t stream) {
-  IEEE_REQUIRE(counts && n_rel_all && ap && first && short_list, "rank_query_metrics: null pointer");
+  IEEE_REQUIRE(counts && ap && first && short_list, "rank_query_metrics: null pointer");
   IEEE_REQUIRE(Q > 0 && G_total > 0 && max_rank >= 1 && shards >= 1 && cap >= 1, "rank_query_metrics: bad shape");
   if (max_rank > G_total) max_rank = (int32_t)G_total;   // rank.py:110-115
-  rank_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ap,
+  rank_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(counts, Q, G_total, shards, cap, max_rank, ap,
                                                                      first, short_list); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -797,7 +797,7 @@ int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_lis
   return IEEE_OK;
 }
 
-int rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                   double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream) {
   IEEE_REQUIRE(workspace != nullptr, "rank_finalize: null workspace");
@@ -806,7 +806,7 @@ int rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, in
   double* ap = per_query_ap ? per_query_ap : reinterpret_cast<double*>(w);
   int32_t* first = per_query_first ? per_query_first : reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8));
   int32_t* is_short = reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8) + align256(size_t(Q) * 4));
-  int rc = rank_query_metrics(counts, n_rel_all, Q, G_total, shards, cap, max_rank, ap, first, is_short, stream);
+  int rc = rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, is_short, stream);
   if (rc) return rc;
   return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, stream);
 }

@@ -129,18 +129,16 @@ class RetrievalEvaluator:
         st.gather(dist, qp, qc, self.labels, self.g_offset)
         if self.world > 1:
             import torch.distributed as dist_
-            rel_all = torch.empty((self.world, Qb, cap), dtype=torch.int64, device=self.device)
-            n_rel_all = torch.empty((self.world, Qb), dtype=torch.int32, device=self.device)
+            # the lists carry their own lengths (last column): one all-gather, then one all-reduce of the counts
+            rel_all = torch.empty((self.world, Qb, cap + 1), dtype=torch.int64, device=self.device)
             dist_.all_gather_into_tensor(rel_all, st.rel, group=self.group)
-            dist_.all_gather_into_tensor(n_rel_all, st.n_rel, group=self.group)
-            st.count(dist, self.G, self.g_offset, rel_all, n_rel_all)
+            st.count(dist, self.G, self.g_offset, rel_all)
             dist_.all_reduce(st.counts, group=self.group)
         else:
-            n_rel_all = st.n_rel
             st.count(dist, self.G, self.g_offset)
         ties += st.flags[1:2]
-        _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), n_rel_all.data_ptr(), Qb, self.g_total, self.world, cap,
-                  self.max_rank, ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
+        _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, self.world, cap, self.max_rank,
+                  ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
         return st
 
     @classmethod
@@ -187,11 +185,29 @@ class RetrievalEvaluator:
                     self._copy = copy_stream(self.device)
                 self._copy.wait_stream(torch.cuda.current_stream())
                 if not qf.is_cuda:                       # queries first: every contraction needs them
-                    q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
-                    with torch.cuda.stream(self._copy):
-                        q_dev.copy_(qf, non_blocking=True)
-                        q_event = self._copy.record_event()
-                    qf = q_dev
+                    if self.world > 1:
+                        # the query set is the same on every rank: each copies 1/N of it over its own PCIe link and
+                        # the slices are all-gathered over NVLink instead of N full host->device copies
+                        import torch.distributed as dist_
+                        rank = dist_.get_rank(self.group)
+                        per = (Q + self.world - 1) // self.world
+                        q_all = torch.empty((self.world * per, qf.shape[1]), dtype=qf.dtype, device=self.device)
+                        mine = q_all[rank * per: (rank + 1) * per]
+                        lo, hi = min(Q, rank * per), min(Q, (rank + 1) * per)
+                        with torch.cuda.stream(self._copy):
+                            if hi > lo:
+                                mine[: hi - lo].copy_(qf[lo:hi], non_blocking=True)
+                            if hi - lo < per:
+                                mine[hi - lo:].zero_()
+                            dist_.all_gather_into_tensor(q_all, mine, group=self.group)
+                            q_event = self._copy.record_event()
+                        qf = q_all[:Q]
+                    else:
+                        q_dev = torch.empty(qf.shape, dtype=qf.dtype, device=self.device)
+                        with torch.cuda.stream(self._copy):
+                            q_dev.copy_(qf, non_blocking=True)
+                            q_event = self._copy.record_event()
+                        qf = q_dev
                 if pending_gallery:
                     self._start_gallery_copies(self._copy)
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
@@ -228,14 +244,9 @@ class RetrievalEvaluator:
             # allocations below) hide behind the tensor-core kernel.
             dist = contraction(0, min(Q, rows))
             TRACE.mark("contraction(block 0) queued")
-            cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready)
+            cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready, self.group if self.world > 1 else None)
             cap_done.synchronize()
             cap = max(int(cap_host.item()), 1)
-            if self.world > 1:
-                import torch.distributed as dist_
-                cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
-                dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
-                cap = int(cap_t.item())
             full = None
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)

@@ -62,10 +62,12 @@ class GalleryLabels:
                 _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
                 self.ready = stream.record_event()         # grouping queued up to here
 
-    def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
+    def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event, group=None):
         """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
         ids (`q_ready`) -- NOT after whatever else the compute stream holds, so the caller can queue the contraction
-        first and the host round trip hides behind it.  Returns (event, pinned int32)."""
+        first and the host round trip hides behind it.  With a process group the per-shard capacities are
+        max-reduced on the same side stream (every rank must size its lists alike for the all-gather).
+        Returns (event, pinned int32)."""
         dev = q_pids.device
         side = side_stream(dev)
         key = dev.index
@@ -77,6 +79,9 @@ class GalleryLabels:
         with torch.cuda.stream(side):
             _lib.call("ieee_rank_list_cap", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
                       self._scratch.data_ptr(), _lib.stream())
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(self._scratch[:1], op=dist.ReduceOp.MAX, group=group)
             host.copy_(self._scratch[:1], non_blocking=True)
             done = side.record_event()
         return done, host
@@ -94,11 +99,11 @@ class RankStages:
 
     def __init__(self, Q: int, cap: int, shards: int, device):
         self.Q, self.cap, self.shards, self.device = Q, cap, shards, device
-        self.rel = torch.empty((Q, cap), dtype=torch.int64, device=device)     # bit pattern of uint64 keys
+        self.rel = torch.empty((Q, cap + 1), dtype=torch.int64, device=device)  # uint64 keys; [:, cap] = list length
         self.junk = torch.empty((Q, cap), dtype=torch.int64, device=device)
         self.n_rel = torch.empty(Q, dtype=torch.int32, device=device)
         self.n_junk = torch.empty(Q, dtype=torch.int32, device=device)
-        self.counts = torch.empty((Q, shards * cap + 1), dtype=torch.int32, device=device)
+        self.counts = torch.empty((Q, shards * cap + 2), dtype=torch.int32, device=device)
         self.flags = torch.zeros(8, dtype=torch.int64, device=device)          # [0] overflow (int32), [1] ties (uint64)
         self.cmc = None
         self.summary = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=device)
@@ -113,22 +118,22 @@ class RankStages:
                   self.rel.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
                   self.flags.data_ptr(), _lib.stream())
 
-    def count(self, distmat, G: int, g_offset: int = 0, rel_all=None, n_rel_all=None):
+    def count(self, distmat, G: int, g_offset: int = 0, rel_all=None):
+        """rel_all: the all-gathered relevant lists [shards, Q, cap + 1] (this rank's own list on one GPU)."""
         rel_all = self.rel if rel_all is None else rel_all
-        n_rel_all = self.n_rel if n_rel_all is None else n_rel_all
         _lib.call("ieee_rank_count", distmat.data_ptr(), distmat.stride(0), self.Q, G, g_offset, self.shards, self.cap,
-                  rel_all.data_ptr(), n_rel_all.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
+                  rel_all.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
                   self.counts.data_ptr(), self.flags.data_ptr() + 8, _lib.stream())
 
-    def finalize(self, G_total: int, max_rank: int, n_rel_all=None, counts=None, ties=None):
-        n_rel_all = self.n_rel if n_rel_all is None else n_rel_all
+    def finalize(self, G_total: int, max_rank: int, counts=None, ties=None):
+        """counts: the all-reduced count table (this rank's own on one GPU)."""
         counts = self.counts if counts is None else counts
         k_eff = min(max_rank, G_total)
         self.cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
         ties_ptr = self.flags.data_ptr() + 8 if ties is None else ties.data_ptr()
-        _lib.call("ieee_rank_finalize", counts.data_ptr(), n_rel_all.data_ptr(), self.Q, G_total, self.shards, self.cap,
-                  max_rank, ties_ptr, self.cmc.data_ptr(), self.summary.data_ptr(), self.ap.data_ptr(),
-                  self.first.data_ptr(), self.ws.data_ptr(), _lib.stream())
+        _lib.call("ieee_rank_finalize", counts.data_ptr(), self.Q, G_total, self.shards, self.cap, max_rank, ties_ptr,
+                  self.cmc.data_ptr(), self.summary.data_ptr(), self.ap.data_ptr(), self.first.data_ptr(),
+                  self.ws.data_ptr(), _lib.stream())
 
     def read_summary(self) -> _lib.EvalSummary:
         raw = self.summary.cpu().numpy().tobytes()      # synchronises

@@ -141,24 +141,27 @@ int ieee_rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int6
 int ieee_rank_list_cap_sync(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* scratch_dev,
                             int32_t* cap_host, ieee_stream_t stream);
 
-/* gather: for each of Q queries, rel[q, 0..n_rel[q]) = packed (orderable distance key << 32 | global gallery
- * index) of the relevant local items (same pid, other camera), junk[q, ...] likewise for the junk items
- * (same pid, same camera, rank.py:136).  `cap` = list capacity per query (>= max_group).  Unsorted.
+/* gather: for each of Q queries, rel[q, 0..n) = packed (orderable distance key << 32 | global gallery index) of
+ * the relevant local items (same pid, other camera), junk[q, ...] likewise for the junk items (same pid, same
+ * camera, rank.py:136).  `cap` = list capacity per query (>= ieee_rank_list_cap).  Unsorted.
+ * rel is uint64[Q, cap + 1]: entry [q, cap] holds the list length, so ONE all-gather of rel moves lists and lengths;
+ * n_rel / n_junk (int32[Q]) receive the lengths as well.  junk is uint64[Q, cap].
  * g_offset = global index of local gallery row 0 (0 on one GPU). */
 int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
                      const int64_t* q_camids, const int64_t* g_camids, const void* group, int64_t g_offset,
                      int32_t cap, uint64_t* rel, int32_t* n_rel, uint64_t* junk, int32_t* n_junk,
                      int32_t* overflow_flag, ieee_stream_t stream);
 
-/* count: thresholds of query q = union over the `shards` relevant lists rel_all[s][q][cap] (the all-gathered
+/* count: thresholds of query q = union over the `shards` relevant lists rel_all[s][q][cap + 1] (the all-gathered
  * buffers; shards = 1 and rel_all = rel on one GPU).  Streams the local distance row once and writes
- * counts[q, k] = #{local kept g : (d, g) <lex T_k} for the k-th smallest threshold, k < n_rel_total[q]
- * (= sum over shards), plus counts[q, shards*cap] = number of local junk items.  counts is
- * int32[Q, shards*cap + 1]; it is summed over shards by the caller (all-reduce) before finalize.
- * ties (int64[1], may be NULL) accumulates bit-equal (threshold, other kept item) pairs. */
+ * counts[q, k] = #{local kept g : (d, g) <lex T_k} for the k-th smallest threshold, k < R[q] (= lengths summed over
+ * shards), plus counts[q, shards*cap] = this shard's number of relevant items (n_rel) and
+ * counts[q, shards*cap + 1] = its number of junk items.  counts is int32[Q, shards*cap + 2]; it is summed over
+ * shards by the caller (all-reduce) before query_metrics / finalize, which read R[q] from it.
+ * ties (uint64[1], may be NULL) accumulates bit-equal (threshold, other kept item) pairs. */
 size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap);
 int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards,
-                    int32_t cap, const uint64_t* rel_all, const int32_t* n_rel_all, const uint64_t* junk,
+                    int32_t cap, const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk,
                     const int32_t* n_junk, int32_t* counts, unsigned long long* ties, ieee_stream_t stream);
 
 /* finalize = ieee_rank_query_metrics (per query) followed by ieee_rank_reduce (over queries); the two halves
@@ -169,15 +172,15 @@ int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int6
  * the query keeps fewer than max_rank gallery items.  G_total = gallery size over all shards.
  * reduce: cmc[0..K') float32 = float32(hits_j) / float32(num_valid) exactly as rank.py:167-168 and
  * mAP = mean(ap) (float64, fixed reduction tree: bitwise reproducible), K' = min(max_rank, G_total). */
-int ieee_rank_query_metrics(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
-                            int32_t cap, int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
+int ieee_rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+                            int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
                             ieee_stream_t stream);
 int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
                      const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, ieee_stream_t stream);
 /* per_query_ap (double[Q]) / per_query_first (int32[Q]) may be NULL.  workspace: ieee_rank_finalize_workspace_bytes(Q). */
 size_t ieee_rank_finalize_workspace_bytes(int64_t Q);
-int ieee_rank_finalize(const int32_t* counts, const int32_t* n_rel_all, int64_t Q, int64_t G_total, int32_t shards,
-                       int32_t cap, int32_t max_rank, const unsigned long long* ties, float* cmc,
+int ieee_rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
+                       int32_t max_rank, const unsigned long long* ties, float* cmc,
                        ieee_eval_summary* summary, double* per_query_ap, int32_t* per_query_first, void* workspace,
                        ieee_stream_t stream);
 

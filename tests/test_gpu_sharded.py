@@ -36,14 +36,13 @@ def test_shard_stages_on_one_gpu(shards):
     stages = [RankStages(Q, cap, shards, dev) for _ in parts]
     for st, (g0, g1, dl, gal) in zip(stages, parts):
         st.gather(dl, qp, qc, gal, g0)
-    rel_all = torch.stack([st.rel for st in stages]).contiguous()
-    n_rel_all = torch.stack([st.n_rel for st in stages]).contiguous()
+    rel_all = torch.stack([st.rel for st in stages]).contiguous()          # what the all-gather produces
     for st, (g0, g1, dl, gal) in zip(stages, parts):
-        st.count(dl, g1 - g0, g0, rel_all, n_rel_all)
+        st.count(dl, g1 - g0, g0, rel_all)
     total = torch.stack([st.counts for st in stages]).sum(0).to(torch.int32).contiguous()
     ties = torch.stack([st.flags[1:2] for st in stages]).sum(0).contiguous()
     fin = stages[0]
-    fin.finalize(G, 20, n_rel_all=n_rel_all, counts=total, ties=ties)
+    fin.finalize(G, 20, counts=total, ties=ties)
     summary = fin.read_summary()
     assert np.array_equal(fin.cmc.cpu().numpy(), cmc_o) and abs(summary.mAP - map_o) < 1e-9
     assert np.array_equal(fin.first.cpu().numpy(), info["first_hit"])
