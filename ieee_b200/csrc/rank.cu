@@ -236,6 +236,13 @@ __host__ __device__ inline CountSmemPlan count_smem_plan(int Rp) {
 
 enum CountMode { COUNT_LUT_PRIVATE = 0, COUNT_LUT_ATOMIC = 1, COUNT_SEARCH_ATOMIC = 2 };
 
+// Table size for a row of G distances: building it costs O(L) per query, so short rows get short tables.
+__host__ __device__ inline int lut_cells_for(int G) {
+  int L = 64;
+  while (L < kLutCells && L * 8 < G) L <<= 1;
+  return L;
+}
+
 struct CountCtx {
   const uint64_t* T;
   const uint32_t* cell;
@@ -244,6 +251,7 @@ struct CountCtx {
   float lo, hi, scale;
   uint32_t kmax;
   int R, trash;
+  int L;                // live cells of the table (power of two <= kLutCells), chosen from the row length
   uint32_t g_offset;
   int ties;
 };
@@ -272,12 +280,12 @@ __device__ __forceinline__ void count_bump(CountCtx& c, int b, int delta) {
   else atomicAdd(&c.hist[b], delta);
 }
 
-// Cell of a distance in the guarded table: index 0 = "before every threshold" (bin 0), 1 .. L = the L cells over
+// Cell of a distance in the guarded table (L = c.L live cells): index 0 = "before every threshold" (bin 0), 1 .. L = the L cells over
 // [lo, hi], L + 1 = "after every threshold" (trash bin).  floor() sends d < lo below 0 and d >> hi beyond L; NaN
 // converts to 0 and lands in cell 1, which holds T_0 and therefore takes the exact path (key order: last).
 __device__ __forceinline__ uint32_t count_cell(const CountCtx& c, float d) {
   int ci = __float2int_rd((d - c.lo) * c.scale);
-  ci = max(min(ci, kLutCells) + 1, 0);
+  ci = max(min(ci, c.L) + 1, 0);
   return c.cell[ci];
 }
 
@@ -404,24 +412,25 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
     T[pos] = me;
   }
-  for (int i = lane; i < kLutCells + 2; i += 32) cell[i] = 0;
+  for (int i = lane; i < lut_cells_for(G) + 2; i += 32) cell[i] = 0;
   __syncwarp();
   for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
   for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;     // own column only: i % 32 == lane
   const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
+  const int L = lut_cells_for(G);
   const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
-  const float scale = use_lut ? ((float)kLutCells - 0.5f) / span : 0.f;
+  const float scale = use_lut ? ((float)L - 0.5f) / span : 0.f;
   if (use_lut) {
     for (int k = lane; k < R; k += 32) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
-      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), kLutCells - 1)], 1u << 20);
+      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), L - 1)], 1u << 20);
     }
     __syncwarp();
     // exclusive scan over the 1024 cells, 32 at a time (lane <-> cell: conflict-free), carry in a register
     int carry = 0;
-    for (int k0 = 1; k0 <= kLutCells; k0 += 32) {
+    for (int k0 = 1; k0 <= L; k0 += 32) {
       const int cnt = (int)(cell[k0 + lane] >> 20);
       int incl = cnt;
 #pragma unroll
@@ -429,12 +438,12 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
       cell[k0 + lane] = (uint32_t)(carry + incl - cnt) | ((uint32_t)cnt << 20);
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) { cell[0] = 0; cell[kLutCells + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
+    if (lane == 0) { cell[0] = 0; cell[L + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
   }
   __syncwarp();
   CountCtx c;
   c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + lane;
-  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1;
+  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
   c.g_offset = (uint32_t)g_offset; c.ties = 0;
   const float* row = distmat + q * ld;
   if (use_lut) count_stream<COUNT_LUT_PRIVATE, 32>(c, row, G, lane);
@@ -542,15 +551,16 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
+  const int L = lut_cells_for(G);
   const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f &&
                        isfinite((float)kLutCells / span) && R < (1 << 11);
-  // (hi - lo) * scale = kLutCells - 0.5: every in-range distance lands in [0, kLutCells) without a clamp, and the map
-  // stays monotone (the -0.5 margin dwarfs fp32 rounding); out-of-range / NaN elements are only masked into range
-  const float scale = use_lut ? ((float)kLutCells - 0.5f) / span : 0.f;
+  // (hi - lo) * scale = L - 0.5: every in-range distance lands in cells [0, L) and the map stays monotone (the -0.5
+  // margin dwarfs fp32 rounding); out-of-range elements fall into the guard cells
+  const float scale = use_lut ? ((float)L - 0.5f) / span : 0.f;
   if (use_lut) {
     for (int k = tid; k < R; k += kCountThreads) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));
-      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), kLutCells - 1)], 1u << 20);
+      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), L - 1)], 1u << 20);
     }
     __syncthreads();
     // exclusive scan of the per-cell counts -> first bin of each cell (kLutCells == 4 * kCountThreads)
@@ -568,15 +578,19 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
     for (int i = 0; i < w; ++i) woff += wsum[i];
     int run = woff + incl - sum;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { cell[1 + tid * 4 + j] = (uint32_t)run | ((uint32_t)v[j] << 20); run += v[j]; }
-    if (tid == 0) { cell[0] = 0; cell[kLutCells + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
+    for (int j = 0; j < 4; ++j) {
+      const int idx = 1 + tid * 4 + j;          // cells beyond L are empty; index L + 1 is the trash guard
+      cell[idx] = (idx == L + 1) ? (uint32_t)(R + 1) : ((uint32_t)run | ((uint32_t)v[j] << 20));
+      run += v[j];
+    }
+    if (tid == 0) { cell[0] = 0; if (L == kLutCells) cell[L + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
   }
   __syncthreads();
 
   // ---- stream the row ---------------------------------------------------------------------------------------
   CountCtx c;
   c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + tid;
-  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1;
+  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
   c.g_offset = (uint32_t)g_offset; c.ties = 0;
   const float* row = distmat + q * ld;
   if (!use_lut) count_stream<COUNT_SEARCH_ATOMIC, kCountThreads>(c, row, G, tid);

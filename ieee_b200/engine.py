@@ -221,9 +221,13 @@ class RetrievalEvaluator:
                 pitch = (self.G + 31) // 32 * 32
                 self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
 
+            gemm_gate = None
+
             def contraction(s, e):
                 qpk = qf_packed(s, e)
                 out = self._block[: e - s]
+                if gemm_gate is not None:
+                    torch.cuda.current_stream().wait_event(gemm_gate)
                 for i, (c0, gpk) in enumerate(self.chunks):
                     if isinstance(gpk, tuple):            # (event, host->device staging tensor): pack on arrival
                         ev, staged = gpk
@@ -239,12 +243,17 @@ class RetrievalEvaluator:
                     torch.cuda.current_stream().wait_event(q_event)
                 return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
 
-            # The contraction of the first block is queued FIRST; the list capacity is then queried on a side stream
-            # that only waits for the gallery grouping and the query ids, so its host round trip (and the host-side
-            # allocations below) hide behind the tensor-core kernel.
-            dist = contraction(0, min(Q, rows))
-            TRACE.mark("contraction(block 0) queued")
+            # The list capacity is queried on a side stream that only waits for the gallery grouping and the query
+            # ids; its host round trip (and the host-side allocations below) hide behind the packing / contraction
+            # that are queued right after.  With several ranks the capacity is max-reduced by NCCL on that side
+            # stream: the persistent contraction kernel owns every SM, so it is held back (a GPU-side event wait, after
+            # the packing) until that small collective has run -- a NCCL kernel squeezed in beside it would take an
+            # SM pair away from one tile cluster for the whole GEMM.
             cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready, self.group if self.world > 1 else None)
+            gemm_gate = cap_done if self.world > 1 else None
+            dist = contraction(0, min(Q, rows))
+            gemm_gate = None
+            TRACE.mark("contraction(block 0) queued")
             cap_done.synchronize()
             cap = max(int(cap_host.item()), 1)
             full = None
