@@ -51,6 +51,18 @@ class Trace:
 
 TRACE = Trace()
 
+# List-capacity memo.  The per-query list capacity (largest identity group among the queried ids) sizes buffers and
+# shared memory, and finding it costs a host round trip (plus, with several ranks, a collective that has to line the
+# ranks up in the middle of a step).  It only depends on the label tensors, so it is remembered per
+# (gallery ids, query ids) tensor identity AND version counter: handing in the same, unmodified tensors again skips the
+# query.  It is a hint, not a trusted value: the gather kernel flags any list that does not fit, and evaluate()
+# then recomputes the capacity and runs again.
+_CAP_MEMO = {}
+
+
+def _tensor_key(t):
+    return (t.data_ptr(), t.numel(), t._version, str(t.device)) if isinstance(t, torch.Tensor) else None
+
 
 def shard_bounds(num_rows: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous gallery slice of ``rank``: [start, stop).  Global index = local index + start, so the
@@ -116,6 +128,7 @@ class RetrievalEvaluator:
         self._block = None
         self._copy = None
         self._host_gallery = None
+        self._label_keys = (_tensor_key(g_pids), _tensor_key(g_camids))
 
     # -- one query block ---------------------------------------------------------------------------------
     def _block_rows(self, Q: int) -> int:
@@ -136,7 +149,8 @@ class RetrievalEvaluator:
             dist_.all_reduce(st.counts, group=self.group)
         else:
             st.count(dist, self.G, self.g_offset)
-        ties += st.flags[1:2]
+        ties[0:1] += st.flags[1:2]
+        ties[1:2] += st.flags[0:1] & 0xFFFFFFFF      # gather's overflow word (needed capacity, 0 = all lists fitted)
         _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, self.world, cap, self.max_rank,
                   ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
         return st
@@ -167,7 +181,7 @@ class RetrievalEvaluator:
             self.chunks.append((c0, (ev, staged)))
         self._host_gallery = None
 
-    def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False):
+    def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False, use_cap_memo: bool = True):
         """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
         `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
         with torch.cuda.device(self.device):
@@ -213,7 +227,7 @@ class RetrievalEvaluator:
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
-            ties = torch.zeros(1, dtype=torch.int64, device=self.device)
+            ties = torch.zeros(2, dtype=torch.int64, device=self.device)        # [tie pairs, list overflow]
             rows = self._block_rows(Q)
             if self._block is None or self._block.shape[0] < rows:
                 # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
@@ -221,13 +235,9 @@ class RetrievalEvaluator:
                 pitch = (self.G + 31) // 32 * 32
                 self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
 
-            gemm_gate = None
-
             def contraction(s, e):
                 qpk = qf_packed(s, e)
                 out = self._block[: e - s]
-                if gemm_gate is not None:
-                    torch.cuda.current_stream().wait_event(gemm_gate)
                 for i, (c0, gpk) in enumerate(self.chunks):
                     if isinstance(gpk, tuple):            # (event, host->device staging tensor): pack on arrival
                         ev, staged = gpk
@@ -243,19 +253,33 @@ class RetrievalEvaluator:
                     torch.cuda.current_stream().wait_event(q_event)
                 return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
 
-            # The list capacity is queried on a side stream that only waits for the gallery grouping and the query
-            # ids; its host round trip (and the host-side allocations below) hide behind the packing / contraction
-            # that are queued right after.  With several ranks the capacity is max-reduced by NCCL on that side
-            # stream: the persistent contraction kernel owns every SM, so it is held back (a GPU-side event wait, after
-            # the packing) until that small collective has run -- a NCCL kernel squeezed in beside it would take an
-            # SM pair away from one tile cluster for the whole GEMM.
-            cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready, self.group if self.world > 1 else None)
-            gemm_gate = cap_done if self.world > 1 else None
-            dist = contraction(0, min(Q, rows))
-            gemm_gate = None
-            TRACE.mark("contraction(block 0) queued")
-            cap_done.synchronize()
-            cap = max(int(cap_host.item()), 1)
+            memo_key = None
+            if use_cap_memo and self._label_keys[0] is not None and _tensor_key(q_pids) is not None:
+                memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
+            cap = _CAP_MEMO.get(memo_key) if memo_key is not None else None
+            if cap is not None:
+                dist = contraction(0, min(Q, rows))
+                TRACE.mark("contraction(block 0) queued (capacity memo hit)")
+            else:
+                # The contraction of the first block is queued FIRST; the capacity is then queried on a side stream
+                # that only waits for the gallery grouping and the query ids, so its host round trip (and the
+                # host-side allocations below) hide behind the tensor-core kernel.
+                dist = contraction(0, min(Q, rows))
+                TRACE.mark("contraction(block 0) queued")
+                cap_done, cap_host = self.labels.list_cap_async(qp, ids_ready)
+                cap_done.synchronize()
+                cap = max(int(cap_host.item()), 1)
+                if self.world > 1:
+                    # every rank must size its lists alike for the all-gather (after the contraction: a NCCL kernel
+                    # beside the persistent GEMM would take an SM pair away from a tile cluster)
+                    import torch.distributed as dist_
+                    cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
+                    dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
+                    cap = int(cap_t.item())
+                if memo_key is not None:
+                    if len(_CAP_MEMO) > 64:
+                        _CAP_MEMO.clear()
+                    _CAP_MEMO[memo_key] = cap
             full = None
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)
@@ -274,9 +298,14 @@ class RetrievalEvaluator:
             _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
                       cmc.data_ptr(), summ.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
-            out = torch.cat([cmc.view(torch.uint8), summ]).cpu().numpy()          # one D2H copy, synchronises
+            out = torch.cat([cmc.view(torch.uint8), summ, ties[1:2].view(torch.uint8)]).cpu().numpy()   # one D2H copy, synchronises
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
-            summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff:].tobytes())
+            summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff: 4 * k_eff + 64].tobytes())
+            overflow = int(out[4 * k_eff + 64:].view(np.int64)[0])
+        if overflow:
+            # a list did not fit the (memoised) capacity: forget the hint and run again with the exact value
+            _CAP_MEMO.pop(memo_key, None)
+            return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False)
         TRACE.report()
         raise_for_status(summary, self.max_rank)
         info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first}

@@ -62,12 +62,10 @@ class GalleryLabels:
                 _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
                 self.ready = stream.record_event()         # grouping queued up to here
 
-    def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event, group=None):
+    def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
         """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
         ids (`q_ready`) -- NOT after whatever else the compute stream holds, so the caller can queue the contraction
-        first and the host round trip hides behind it.  With a process group the per-shard capacities are
-        max-reduced on the same side stream (every rank must size its lists alike for the all-gather).
-        Returns (event, pinned int32)."""
+        first and the host round trip hides behind it.  Returns (event, pinned int32)."""
         dev = q_pids.device
         side = side_stream(dev)
         key = dev.index
@@ -79,9 +77,6 @@ class GalleryLabels:
         with torch.cuda.stream(side):
             _lib.call("ieee_rank_list_cap", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
                       self._scratch.data_ptr(), _lib.stream())
-            if group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(self._scratch[:1], op=dist.ReduceOp.MAX, group=group)
             host.copy_(self._scratch[:1], non_blocking=True)
             done = side.record_event()
         return done, host

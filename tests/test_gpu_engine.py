@@ -62,3 +62,23 @@ def test_streamed_host_gallery_equals_resident():
     assert torch.equal(i1["distmat"], i2["distmat"]) and np.array_equal(c1, c2) and m1 == m2
     c3, m3 = evaluate(s.qf, s.gf, s.q_pids, s.g_pids, s.q_camids, s.g_camids, verbose=False)      # pageable host tensors
     assert np.array_equal(c1, c3) and m1 == m3
+
+
+def test_capacity_memo_is_checked_not_trusted():
+    """The list-capacity memo is keyed by label tensor identity + version; a stale (too small) hint is caught by the
+    gather kernel's overflow flag and the evaluation is redone with the exact capacity."""
+    from ieee_b200 import engine
+    s = make_retrieval_set(200, 1500, 20, 3, dim=128, sigma=2.0, seed=9)
+    dev = torch.device("cuda")
+    lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.q_camids, s.g_pids, s.g_camids)]
+    ev = RetrievalEvaluator(s.gf.cuda(), lab[2], lab[3])
+    c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    key = [k for k in engine._CAP_MEMO if k[0] == ev._label_keys][0]
+    assert engine._CAP_MEMO[key] == i1["cap"]
+    c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])              # memo hit: same result, no capacity query
+    assert np.array_equal(c1, c2) and m1 == m2
+    engine._CAP_MEMO[key] = 2                                            # poison the hint: far too small
+    c3, m3, i3 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    assert np.array_equal(c1, c3) and m1 == m3 and i3["cap"] == i1["cap"]
+    lab[0][0] += 0                                                       # in-place op bumps the version: key changes
+    assert engine._tensor_key(lab[0]) != key[1]
