@@ -60,6 +60,21 @@ TRACE = Trace()
 _CAP_MEMO = {}
 
 
+_STAGE_POOL = {}
+
+
+def _stages_for(Qb, cap, world, device):
+    """Stage buffers are reused across evaluations of the same shape (all work on them is ordered by the compute
+    stream); creating the dozen small tensors costs more host time than the kernels take to launch."""
+    key = (Qb, cap, world, str(device))
+    st = _STAGE_POOL.get(key)
+    if st is None:
+        if len(_STAGE_POOL) > 8:
+            _STAGE_POOL.clear()
+        st = _STAGE_POOL[key] = RankStages(Qb, cap, world, device)
+    return st
+
+
 def _tensor_key(t):
     return (t.data_ptr(), t.numel(), t._version, str(t.device)) if isinstance(t, torch.Tensor) else None
 
@@ -137,7 +152,7 @@ class RetrievalEvaluator:
 
     def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties):
         Qb = dist.shape[0]
-        st = RankStages(Qb, cap, self.world, self.device)
+        st = _stages_for(Qb, cap, self.world, self.device)
         torch.cuda.current_stream().wait_event(self.labels.ready)
         st.gather(dist, qp, qc, self.labels, self.g_offset)
         if self.world > 1:
