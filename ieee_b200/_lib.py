@@ -20,7 +20,7 @@ i64, i32, sz, vp, f32 = C.c_int64, C.c_int32, C.c_size_t, C.c_void_p, C.c_float
 
 class EvalSummary(C.Structure):
     _fields_ = [("mAP", C.c_double), ("sum_ap", C.c_double), ("num_valid", i64), ("num_ties", i64),
-                ("num_short", i64), ("max_rank", i32), ("status", i32), ("reserved", i64 * 2)]
+                ("num_short", i64), ("max_rank", i32), ("status", i32), ("list_overflow", i64), ("mINP", C.c_double)]
 
 
 # name -> (restype, argtypes); must list every symbol include/ieee_b200.h declares (tests/test_abi.py checks)
@@ -44,12 +44,18 @@ SIGNATURES = {
     "ieee_rank_gather": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "ieee_rank_count_smem_bytes": (sz, [i32, i32]),
     "ieee_rank_count": (C.c_int, [vp, i64, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
-    "ieee_rank_query_metrics": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp]),
-    "ieee_rank_reduce": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "ieee_rank_query_metrics": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "ieee_rank_reduce": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]),
     "ieee_rank_finalize_workspace_bytes": (sz, [i64]),
     "ieee_rank_finalize": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "ieee_eval_workspace_bytes": (sz, [i64, i64, i32]),
     "ieee_eval_market1501": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
+    "ieee_retrieve_workspace_bytes": (sz, [i64, i64, i64, C.c_int, i32]),
+    "ieee_retrieve_eval": (C.c_int, [vp, i64, vp, i64, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32,
+                                     C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "ieee_retrieve_prepared_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
+    "ieee_retrieve_eval_prepared": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, vp, vp, vp, i32, i32,
+                                              C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "ieee_topk": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
     "ieee_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
     "ieee_rerank_workspace_bytes": (sz, [i64, i64, i32, i32]),

@@ -51,12 +51,15 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
                int32_t* counts, unsigned long long* ties, cudaStream_t stream);
 size_t rank_finalize_workspace_bytes(int64_t Q);
 int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
-                       int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, cudaStream_t stream);
+                       int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, double* inp,
+                       cudaStream_t stream);
 int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
-                const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, cudaStream_t stream);
+                const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, const double* inp,
+                const int32_t* overflow, cudaStream_t stream);
 int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
-                  double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream);
+                  double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream,
+                  const int32_t* overflow = nullptr);
 int topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
          const int64_t* q_camids, const int64_t* g_pids, const int64_t* g_camids, int32_t k, int32_t* idx, float* val,
          cudaStream_t stream);
@@ -238,17 +241,18 @@ int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int6
 
 int ieee_rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards,
                             int32_t cap, int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
-                            ieee_stream_t stream) {
+                            double* inp, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, short_list, (cudaStream_t)stream);
+  return rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, short_list, inp, (cudaStream_t)stream);
 }
 
 int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
-                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, ieee_stream_t stream) {
+                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, const double* inp,
+                     ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_reduce(ap, first, short_list, Q, max_rank, ties, cmc, summary, (cudaStream_t)stream);
+  return rank_reduce(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, nullptr, (cudaStream_t)stream);
 }
 
 size_t ieee_rank_finalize_workspace_bytes(int64_t Q) { return Q > 0 ? rank_finalize_workspace_bytes(Q) : 0; }
@@ -317,6 +321,99 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
   return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
+}
+
+// ---- retrieval + evaluation in one call ----------------------------------------------------------------
+static size_t retrieve_rank_bytes(int64_t Q, int32_t cap) {
+  size_t b = 256;                                  // cap scratch + overflow flag + ties
+  b += 2 * align256(size_t(Q) * (cap + 1) * 8);    // rel (+ embedded count), junk
+  b += 2 * align256(size_t(Q) * 4);                // n_rel, n_junk
+  b += align256(size_t(Q) * (cap + 2) * 4);        // counts
+  b += align256(rank_finalize_workspace_bytes(Q));
+  return b;
+}
+
+size_t ieee_retrieve_prepared_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap) {
+  if (Q <= 0 || D <= 0) return 0;
+  if (cap <= 0) cap = 4096;
+  return align256(ieee_packed_bytes(Q, D, precision)) + retrieve_rank_bytes(Q, cap) + 256;
+}
+
+size_t ieee_retrieve_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision, int32_t cap) {
+  if (Q <= 0 || G <= 0 || D <= 0) return 0;
+  if (cap <= 0) cap = (int32_t)(G < 4096 ? G : 4096);
+  return align256(ieee_packed_bytes(G, D, precision)) + align256(gallery_group_bytes(G)) +
+         ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap);
+}
+
+int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
+                                int precision, const void* g_packed, const void* group, int64_t G, const int64_t* q_pids,
+                                const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank, int32_t cap,
+                                int32_t* cap_host_out, float* distmat, int64_t ld, float* cmc, ieee_eval_summary* summary,
+                                double* per_query_ap, int32_t* per_query_first, void* workspace, size_t workspace_bytes,
+                                ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(qf && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace,
+               "retrieve: null pointer");
+  IEEE_REQUIRE(Q > 0 && G > 0 && D > 0 && ld >= G && max_rank >= 1, "retrieve: bad shape Q=%lld G=%lld D=%lld ld=%lld max_rank=%d",
+               (long long)Q, (long long)G, (long long)D, (long long)ld, max_rank);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve: workspace must be 256-byte aligned");
+  Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
+  void* q_packed = a.take(ieee_packed_bytes(Q, D, precision));
+  int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
+  if (!q_packed || !scratch) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, q_packed, stream))) return rc;
+  if (cap <= 0) {
+    int32_t need = 0;
+    if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
+    cap = need < 1 ? 1 : need;
+  }
+  if (cap_host_out) *cap_host_out = cap;
+  uint64_t* rel = static_cast<uint64_t*>(a.take(size_t(Q) * (cap + 1) * 8));
+  uint64_t* junk = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
+  int32_t* n_rel = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  int32_t* n_junk = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  int32_t* counts = static_cast<int32_t*>(a.take(size_t(Q) * (cap + 2) * 4));
+  void* fws = a.take(rank_finalize_workspace_bytes(Q));
+  if (!rel || !junk || !n_rel || !n_junk || !counts || !fws) {
+    set_error("retrieve: workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
+              ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap), cap);
+    return IEEE_ERR_WORKSPACE;
+  }
+  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, stream_))) return rc;
+  IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
+  unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
+  if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
+  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
+  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, per_query_ap, per_query_first, fws, stream,
+                       scratch + 1);
+}
+
+int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg, int dtype, int64_t Q, int64_t G, int64_t D,
+                       int metric, int normalize, int precision, const int64_t* q_pids, const int64_t* g_pids,
+                       const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank, int32_t cap,
+                       int32_t* cap_host_out, float* distmat, int64_t ld, float* cmc, ieee_eval_summary* summary,
+                       double* per_query_ap, int32_t* per_query_first, void* workspace, size_t workspace_bytes,
+                       ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(gf && g_pids && workspace, "retrieve: null pointer");
+  IEEE_REQUIRE(Q > 0 && G > 0 && D > 0, "retrieve: bad shape Q=%lld G=%lld D=%lld", (long long)Q, (long long)G, (long long)D);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve: workspace must be 256-byte aligned");
+  Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
+  void* g_packed = a.take(ieee_packed_bytes(G, D, precision));
+  void* group = a.take(gallery_group_bytes(G));
+  if (!g_packed || !group) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  // labels first: the grouping is three tiny kernels, and a capacity query (cap <= 0) only waits for them
+  if ((rc = gallery_group(g_pids, G, group, stream))) return rc;
+  if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, g_packed, stream))) return rc;
+  const size_t used = align256(a.off);
+  return ieee_retrieve_eval_prepared(qf, ldq, dtype, Q, D, metric, normalize, precision, g_packed, group, G, q_pids, q_camids,
+                                     g_camids, max_rank, cap, cap_host_out, distmat, ld, cmc, summary, per_query_ap,
+                                     per_query_first, static_cast<uint8_t*>(workspace) + used, workspace_bytes - used, stream_);
 }
 
 int ieee_topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,

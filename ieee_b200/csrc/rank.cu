@@ -713,13 +713,19 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
 __global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restrict__ counts,
                                                           int64_t Q, int64_t G_total, int shards, int cap, int max_rank,
                                                           double* __restrict__ ap, int32_t* __restrict__ first,
-                                                          int32_t* __restrict__ is_short) {
+                                                          int32_t* __restrict__ is_short, double* __restrict__ inp) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   const int stride = shards * cap + 2;
   const int32_t* c = counts + q * stride;
   const int R = c[stride - 2];            // relevant items over all shards (summed with the counts)
-  if (R == 0) { ap[q] = 0.0; first[q] = -1; is_short[q] = 0; return; }
+  if (R == 0) {
+    ap[q] = 0.0; first[q] = -1; is_short[q] = 0;
+    if (inp) inp[q] = 0.0;
+    return;
+  }
+  // inverse negative penalty (README.rst:45, Ye et al. TPAMI 2021): R / (1-based rank of the hardest relevant item)
+  if (inp) inp[q] = (double)R / ((double)c[R - 1] + 1.0);
   // rank.py:155-160: AP = (1/R) sum_k (k+1) / (pos_k + 1), float64
   double s = 0.0;
   for (int k = 0; k < R; ++k) s += (double)(k + 1) / ((double)c[k] + 1.0);
@@ -732,28 +738,33 @@ __global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restri
 __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restrict__ ap, const int32_t* __restrict__ first,
                                                             const int32_t* __restrict__ is_short, int64_t Q, int max_rank,
                                                             const unsigned long long* __restrict__ ties, float* __restrict__ cmc,
-                                                            ieee_eval_summary* __restrict__ summary) {
+                                                            ieee_eval_summary* __restrict__ summary,
+                                                            const double* __restrict__ inp,
+                                                            const int32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t rs_raw[];
-  double* sd = reinterpret_cast<double*>(rs_raw);                 // [1024]
-  int32_t* hfirst = reinterpret_cast<int32_t*>(sd + 1024);        // [max_rank + 1]
+  double* sd = reinterpret_cast<double*>(rs_raw);                 // [1024] AP partial sums
+  double* si = sd + 1024;                                         // [1024] INP partial sums
+  int32_t* hfirst = reinterpret_cast<int32_t*>(si + 1024);        // [max_rank + 1]
   __shared__ long long s_valid, s_short;
   const int tid = threadIdx.x;
   for (int i = tid; i <= max_rank; i += 1024) hfirst[i] = 0;
   if (tid == 0) { s_valid = 0; s_short = 0; }
   __syncthreads();
   // fixed assignment of queries to threads + fixed tree => the fp64 sum does not depend on scheduling
-  double acc = 0.0;
+  double acc = 0.0, acc_inp = 0.0;
   long long nv = 0, ns = 0;
   for (int64_t q = tid; q < Q; q += 1024) {
     const int f = first[q];
     if (f >= 0) {
       acc += ap[q];
+      if (inp) acc_inp += inp[q];
       ++nv;
       ns += is_short[q];
       atomicAdd(&hfirst[f < max_rank ? f : max_rank], 1);   // shared int32 atomics: native, cheap
     }
   }
   sd[tid] = acc;
+  si[tid] = acc_inp;
   // counts: warp shuffle first, then one shared atomic per warp (1024 threads CAS-looping on one 64-bit shared
   // word cost 40 us here)
   for (int o = 16; o > 0; o >>= 1) {
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restr
   }
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
-    if (tid < o) sd[tid] += sd[tid + o];
+    if (tid < o) { sd[tid] += sd[tid + o]; si[tid] += si[tid + o]; }
     __syncthreads();
   }
   if (tid == 0) {
@@ -784,45 +795,52 @@ __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restr
     summary->num_short = s_short;
     summary->max_rank = max_rank;
     summary->status = valid == 0 ? IEEE_ERR_NO_VALID_QUERY : (s_short > 0 ? IEEE_ERR_SHORT_RANK_LIST : IEEE_OK);
-    summary->reserved[0] = summary->reserved[1] = 0;
+    summary->list_overflow = overflow ? (int64_t)*overflow : 0;
+    summary->mINP = (inp && valid > 0) ? si[0] / (double)valid : 0.0;
   }
 }
 
-size_t rank_finalize_workspace_bytes(int64_t Q) { return align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4); }
+size_t rank_finalize_workspace_bytes(int64_t Q) { return 2 * align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4); }
 
 int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
-                       int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, cudaStream_t stream) {
+                       int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, double* inp,
+                       cudaStream_t stream) {
   IEEE_REQUIRE(counts && ap && first && short_list, "rank_query_metrics: null pointer");
   IEEE_REQUIRE(Q > 0 && G_total > 0 && max_rank >= 1 && shards >= 1 && cap >= 1, "rank_query_metrics: bad shape");
   if (max_rank > G_total) max_rank = (int32_t)G_total;   // rank.py:110-115
   rank_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(counts, Q, G_total, shards, cap, max_rank, ap,
-                                                                     first, short_list); count_launch();
+                                                                     first, short_list, inp); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
 
 int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
-                const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, cudaStream_t stream) {
+                const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, const double* inp,
+                const int32_t* overflow, cudaStream_t stream) {
   IEEE_REQUIRE(ap && first && short_list && cmc && summary, "rank_reduce: null pointer");
   IEEE_REQUIRE(Q > 0 && max_rank >= 1 && max_rank <= 8192, "rank_reduce: bad shape (max_rank=%d)", max_rank);
-  const size_t smem = 1024 * 8 + size_t(max_rank + 1) * 4;
-  rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary); count_launch();
+  const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
+  if (smem > 48 * 1024)
+    IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, overflow); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
 
 int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
-                  double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream) {
+                  double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream,
+                  const int32_t* overflow) {
   IEEE_REQUIRE(workspace != nullptr, "rank_finalize: null workspace");
   if (max_rank > G_total) max_rank = (int32_t)G_total;   // rank.py:110-115
   uint8_t* w = static_cast<uint8_t*>(workspace);
   double* ap = per_query_ap ? per_query_ap : reinterpret_cast<double*>(w);
   int32_t* first = per_query_first ? per_query_first : reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8));
   int32_t* is_short = reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8) + align256(size_t(Q) * 4));
-  int rc = rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, is_short, stream);
+  double* inp = reinterpret_cast<double*>(w + align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4));
+  int rc = rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, is_short, inp, stream);
   if (rc) return rc;
-  return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, stream);
+  return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, inp, overflow, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -75,6 +75,25 @@ def _stages_for(Qb, cap, world, device):
     return st
 
 
+_FUSED_POOL = {}
+
+
+def _fused_buffers(Q, D, precision, cap, k_eff, device):
+    """Workspace + result block of the one-call path, reused per shape (stream-ordered like the stage pool)."""
+    key = (Q, D, precision, cap, k_eff, str(device))
+    buf = _FUSED_POOL.get(key)
+    if buf is None:
+        if len(_FUSED_POOL) > 8:
+            _FUSED_POOL.clear()
+        lib = _lib.load()
+        ws = torch.empty(lib.ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap), dtype=torch.uint8, device=device)
+        res_off = (4 * k_eff + 7) // 8 * 8                      # [cmc float32[k_eff] | pad | ieee_eval_summary]
+        res = torch.empty(res_off + C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=device)
+        res_host = torch.empty(res.shape, dtype=torch.uint8, pin_memory=True)
+        buf = _FUSED_POOL[key] = (ws, res, res_off, res_host)
+    return buf
+
+
 def _tensor_key(t):
     return (t.data_ptr(), t.numel(), t._version, str(t.device)) if isinstance(t, torch.Tensor) else None
 
@@ -150,7 +169,7 @@ class RetrievalEvaluator:
         rows = max(128, int(self.block_bytes // (4 * max(self.G, 1))) // 128 * 128)
         return min(Q, rows)
 
-    def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties):
+    def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties, inp):
         Qb = dist.shape[0]
         st = _stages_for(Qb, cap, self.world, self.device)
         torch.cuda.current_stream().wait_event(self.labels.ready)
@@ -167,7 +186,7 @@ class RetrievalEvaluator:
         ties[0:1] += st.flags[1:2]
         ties[1:2] += st.flags[0:1] & 0xFFFFFFFF      # gather's overflow word (needed capacity, 0 = all lists fitted)
         _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, self.world, cap, self.max_rank,
-                  ap.data_ptr(), first.data_ptr(), short.data_ptr(), _lib.stream())
+                  ap.data_ptr(), first.data_ptr(), short.data_ptr(), inp.data_ptr(), _lib.stream())
         return st
 
     @classmethod
@@ -196,9 +215,66 @@ class RetrievalEvaluator:
             self.chunks.append((c0, (ev, staged)))
         self._host_gallery = None
 
-    def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False, use_cap_memo: bool = True):
+    def _evaluate_one_call(self, qf, q_pids, q_camids, return_distmat, use_cap_memo):
+        """One GPU, gallery packed in HBM, queries in HBM, one distance block: the whole evaluation is ONE foreign
+        call (ieee_retrieve_eval_prepared enqueues pack -> contraction -> gather -> count -> metrics -> reduce back to
+        back from C) and one device->host copy of (cmc, summary)."""
+        with torch.cuda.device(self.device):
+            Q, D = qf.shape
+            if qf.stride(1) != 1:
+                qf = qf.contiguous()
+            qp = _as_device(q_pids, torch.int64, self.device)
+            qc = _as_device(q_camids, torch.int64, self.device)
+            memo_key = None
+            if use_cap_memo and self._label_keys[0] is not None and _tensor_key(q_pids) is not None:
+                memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
+            cap = _CAP_MEMO.get(memo_key, 0) if memo_key is not None else 0
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.labels.ready)
+            if cap <= 0:
+                # sizing pass: the capacity query synchronises once; later calls with the same labels skip it
+                cap = self.labels.list_cap(qp)
+                if memo_key is not None:
+                    if len(_CAP_MEMO) > 64:
+                        _CAP_MEMO.clear()
+                    _CAP_MEMO[memo_key] = cap
+            k_eff = min(self.max_rank, self.g_total)
+            prec = _lib.PRECISIONS[self.precision]
+            ws, res, res_off, res_host = _fused_buffers(Q, D, prec, cap, k_eff, self.device)
+            pitch = (self.G + 31) // 32 * 32
+            if self._block is None or self._block.shape[0] < Q:
+                self._block = torch.empty((Q, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
+            ap = torch.empty(Q, dtype=torch.float64, device=self.device)
+            first = torch.empty(Q, dtype=torch.int32, device=self.device)
+            gpk = self.chunks[0][1]
+            _lib.call("ieee_retrieve_eval_prepared", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
+                      _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
+                      self.G, qp.data_ptr(), qc.data_ptr(), self.labels.camids.data_ptr(), self.max_rank, cap, None,
+                      self._block.data_ptr(), self._block.stride(0), res.data_ptr(), res.data_ptr() + res_off,
+                      ap.data_ptr(), first.data_ptr(), ws.data_ptr(), ws.numel(), cur.cuda_stream)
+            res_host.copy_(res, non_blocking=True)
+            cur.synchronize()
+            out = res_host.numpy()
+            cmc_host = out[: 4 * k_eff].view(np.float32).copy()
+            summary = _lib.EvalSummary.from_buffer_copy(out[res_off: res_off + 64].tobytes())
+        if summary.list_overflow:
+            _CAP_MEMO.pop(memo_key, None)        # stale hint: size the lists again (exact value, so this ends)
+            return self._evaluate_one_call(qf, q_pids, q_camids, return_distmat, use_cap_memo)
+        raise_for_status(summary, self.max_rank)
+        info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first,
+                "mINP": float(summary.mINP)}
+        if return_distmat:
+            info["distmat"] = self._block[:Q].clone()
+        return cmc_host, float(summary.mAP), info
+
+    def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False, use_cap_memo: bool = True,
+                 one_call: bool = True):
         """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
         `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
+        if (one_call and self.world == 1 and qf.is_cuda and self._host_gallery is None and len(self.chunks) == 1
+                and isinstance(self.chunks[0][1], PackedFeatures) and 0 < qf.shape[0] <= self._block_rows(qf.shape[0])
+                and qf.dtype in _lib.DTYPES):
+            return self._evaluate_one_call(qf, q_pids, q_camids, return_distmat, use_cap_memo)
         with torch.cuda.device(self.device):
             TRACE.mark("evaluate: start")
             Q = qf.shape[0]
@@ -242,6 +318,7 @@ class RetrievalEvaluator:
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
+            inp = torch.empty(Q, dtype=torch.float64, device=self.device)
             ties = torch.zeros(2, dtype=torch.int64, device=self.device)        # [tie pairs, list overflow]
             rows = self._block_rows(Q)
             if self._block is None or self._block.shape[0] < rows:
@@ -300,7 +377,7 @@ class RetrievalEvaluator:
                 e = min(Q, s + rows)
                 if s > 0:
                     dist = contraction(s, e)
-                self._rank_block(dist, qp[s:e], qc[s:e], cap, ap[s:e], first[s:e], short[s:e], ties)
+                self._rank_block(dist, qp[s:e], qc[s:e], cap, ap[s:e], first[s:e], short[s:e], ties, inp[s:e])
                 if return_distmat:
                     full = dist.clone() if full is None else torch.cat([full, dist], 0)
             if self.world > 1:
@@ -311,7 +388,7 @@ class RetrievalEvaluator:
             summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
             TRACE.mark("rank stages done")
             _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
-                      cmc.data_ptr(), summ.data_ptr(), _lib.stream())
+                      cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
             out = torch.cat([cmc.view(torch.uint8), summ, ties[1:2].view(torch.uint8)]).cpu().numpy()   # one D2H copy, synchronises
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
@@ -320,10 +397,11 @@ class RetrievalEvaluator:
         if overflow:
             # a list did not fit the (memoised) capacity: forget the hint and run again with the exact value
             _CAP_MEMO.pop(memo_key, None)
-            return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False)
+            return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False, one_call=one_call)
         TRACE.report()
         raise_for_status(summary, self.max_rank)
-        info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first}
+        info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first,
+                "mINP": float(summary.mINP)}
         if return_distmat:
             info["distmat"] = full
         return cmc_host, float(summary.mAP), info

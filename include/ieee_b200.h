@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define IEEE_B200_ABI_VERSION 1
+#define IEEE_B200_ABI_VERSION 2
 
 typedef void* ieee_stream_t; /* cudaStream_t */
 
@@ -124,7 +124,10 @@ typedef struct {
   int64_t num_short;       /* valid queries that keep fewer than max_rank gallery items                 */
   int32_t max_rank;        /* effective K' = min(max_rank, G_total) (rank.py:110-115)                   */
   int32_t status;          /* IEEE_OK / IEEE_ERR_NO_VALID_QUERY / IEEE_ERR_SHORT_RANK_LIST              */
-  int64_t reserved[2];
+  int64_t list_overflow;   /* 0, or the list capacity a query needed when it exceeded the caller's `cap` hint
+                              (ieee_retrieve_eval*: every other field is then meaningless, call again)     */
+  double mINP;             /* mean inverse negative penalty over valid queries: R / (1-based rank of the hardest
+                              relevant item among the kept ones) (README.rst:45; Ye et al., TPAMI 2021)     */
 } ieee_eval_summary;
 
 /* Group the (local) gallery by identity once: the blob holds an open-addressing hash table pid -> (offset, count)
@@ -174,9 +177,10 @@ int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int6
  * mAP = mean(ap) (float64, fixed reduction tree: bitwise reproducible), K' = min(max_rank, G_total). */
 int ieee_rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                             int32_t max_rank, double* ap, int32_t* first, int32_t* short_list,
-                            ieee_stream_t stream);
+                            double* inp /* double[Q] inverse negative penalty, may be NULL */, ieee_stream_t stream);
 int ieee_rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
-                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, ieee_stream_t stream);
+                     const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
+                     const double* inp /* may be NULL: mINP = 0 */, ieee_stream_t stream);
 /* per_query_ap (double[Q]) / per_query_first (int32[Q]) may be NULL.  workspace: ieee_rank_finalize_workspace_bytes(Q). */
 size_t ieee_rank_finalize_workspace_bytes(int64_t Q);
 int ieee_rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
@@ -193,6 +197,38 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
                          const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
                          int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
                          ieee_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Retrieval + evaluation in ONE call: the tail of Engine._evaluate (engine.py:391-417) --
+ * [normalise] -> distance matrix -> Market-1501 CMC / mAP -- enqueued back to back on `stream` from C, so a
+ * binding pays one foreign call per evaluation instead of one per kernel.
+ *
+ * ieee_retrieve_eval           raw query AND gallery features + labels in, (cmc, summary) out.
+ * ieee_retrieve_eval_prepared  the gallery side was prepared once (ieee_pack_features + ieee_gallery_group)
+ *                              and is reused for every query set.
+ * cap > 0  : list-capacity HINT (e.g. the value a previous call reported); fully asynchronous.  If a query needs
+ *            more, summary->list_overflow holds the needed capacity and the other results are meaningless.
+ * cap <= 0 : the capacity is queried first (one stream synchronisation, ieee_rank_list_cap_sync) and written to
+ *            *cap_host_out when that is not NULL.
+ * distmat  : float32 [Q, ld] scratch for the distance block, ld >= G (ld % 32 == 0 keeps the TMA-store epilogue);
+ *            holds the distance matrix on return (compute_distance_matrix's result, distance.py:6).
+ * cmc: float[max_rank] device; summary: device; per_query_ap (double[Q]) / per_query_first (int32[Q]) may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ieee_retrieve_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision, int32_t cap /* 0 = min(G, 4096) */);
+int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg, int dtype, int64_t Q, int64_t G,
+                       int64_t D, int metric, int normalize, int precision, const int64_t* q_pids,
+                       const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
+                       int32_t cap, int32_t* cap_host_out, float* distmat, int64_t ld, float* cmc,
+                       ieee_eval_summary* summary, double* per_query_ap, int32_t* per_query_first, void* workspace,
+                       size_t workspace_bytes, ieee_stream_t stream);
+size_t ieee_retrieve_prepared_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap);
+int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
+                                int precision, const void* g_packed, const void* group, int64_t G,
+                                const int64_t* q_pids, const int64_t* q_camids, const int64_t* g_camids,
+                                int32_t max_rank, int32_t cap, int32_t* cap_host_out, float* distmat, int64_t ld,
+                                float* cmc, ieee_eval_summary* summary, double* per_query_ap,
+                                int32_t* per_query_first, void* workspace, size_t workspace_bytes,
+                                ieee_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Junk-masked top-k ranked list: the first k entries of rank.py:117 + :136-140 per query (what

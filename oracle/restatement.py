@@ -161,6 +161,27 @@ def metrics_from_positions(positions, max_rank, num_g):
     return cmc, float(np.mean(aps)), len(aps)
 
 
+def mean_inverse_negative_penalty(distmat, q_pids, g_pids, q_camids, g_camids, stable: bool = True) -> float:
+    """mINP.  The reference only NAMES this metric (README.rst:45, pointing at Ye et al., TPAMI 2021 and
+    github.com/mangye16/ReID-Survey); it has no code for it, so this restates the published definition on top of the
+    reference's own ranked list (rank.py:117,136-144): for every valid query, INP = R / (1-based position of the
+    hardest, i.e. last, relevant item among the kept ones); mINP = mean over valid queries.  Parity unpinned by any
+    reference vector (there is none); pinned only to kept_positions() below by tests/test_oracle.py."""
+    distmat = np.asarray(distmat)
+    order = _argsort_rows(distmat, stable)
+    g_pids, g_camids = np.asarray(g_pids), np.asarray(g_camids)
+    inps = []
+    for q in range(distmat.shape[0]):
+        o = order[q]
+        keep = ~((g_pids[o] == q_pids[q]) & (g_camids[o] == q_camids[q]))
+        raw = (g_pids[o] == q_pids[q])[keep]
+        if not raw.any():
+            continue
+        hard = int(np.nonzero(raw)[0].max())
+        inps.append(float(raw.sum()) / (hard + 1.0))
+    return float(np.mean(inps)) if inps else 0.0
+
+
 def topk_kept(distmat, q_pids, g_pids, q_camids, g_camids, k, stable: bool = True):
     """The first k entries of each query's junk-filtered ranked list (rank.py:117,136-140;
     what torchreid/utils/reidtools.py:49,111 walks).  Returns (idx int64 [Q,k], dist [Q,k]);

@@ -64,7 +64,8 @@ def test_streamed_host_gallery_equals_resident():
     assert np.array_equal(c1, c3) and m1 == m3
 
 
-def test_capacity_memo_is_checked_not_trusted():
+@pytest.mark.parametrize("one_call", [True, False])
+def test_capacity_memo_is_checked_not_trusted(one_call):
     """The list-capacity memo is keyed by label tensor identity + version; a stale (too small) hint is caught by the
     gather kernel's overflow flag and the evaluation is redone with the exact capacity."""
     from ieee_b200 import engine
@@ -72,13 +73,43 @@ def test_capacity_memo_is_checked_not_trusted():
     dev = torch.device("cuda")
     lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.q_camids, s.g_pids, s.g_camids)]
     ev = RetrievalEvaluator(s.gf.cuda(), lab[2], lab[3])
-    c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)
     key = [k for k in engine._CAP_MEMO if k[0] == ev._label_keys][0]
     assert engine._CAP_MEMO[key] == i1["cap"]
-    c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])              # memo hit: same result, no capacity query
+    c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)              # memo hit: same result, no capacity query
     assert np.array_equal(c1, c2) and m1 == m2
     engine._CAP_MEMO[key] = 2                                            # poison the hint: far too small
-    c3, m3, i3 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    c3, m3, i3 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)
     assert np.array_equal(c1, c3) and m1 == m3 and i3["cap"] == i1["cap"]
     lab[0][0] += 0                                                       # in-place op bumps the version: key changes
     assert engine._tensor_key(lab[0]) != key[1]
+
+
+def test_one_call_path_equals_staged_path():
+    """ieee_retrieve_eval_prepared (one foreign call per evaluation) == the staged path kernel by kernel; mINP vs the
+    oracle's sort form on the GPU's own distance bits."""
+    s = make_retrieval_set(333, 2500, 45, 5, dim=320, sigma=2.5, seed=77, distractor_frac=0.15)
+    ev = RetrievalEvaluator(s.gf.cuda(), s.g_pids, s.g_camids)
+    c1, m1, i1 = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True, one_call=True)
+    c2, m2, i2 = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True, one_call=False)
+    assert torch.equal(i1["distmat"], i2["distmat"])
+    assert np.array_equal(c1, c2) and m1 == m2 and i1["mINP"] == i2["mINP"] and i1["num_ties"] == i2["num_ties"]
+    assert torch.equal(i1["first"], i2["first"]) and torch.equal(i1["ap"], i2["ap"])
+    d = i1["distmat"].cpu().numpy()
+    cmc_o, map_o = oracle_eval(s, distmat=d)
+    assert np.array_equal(c1, cmc_o) and abs(m1 - map_o) < 1e-9
+    minp_o = R.mean_inverse_negative_penalty(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert abs(i1["mINP"] - minp_o) < 1e-12
+
+
+def test_one_call_path_checks_the_capacity_hint():
+    from ieee_b200 import engine
+    s = make_retrieval_set(150, 1200, 15, 3, dim=128, sigma=2.0, seed=10)
+    dev = torch.device("cuda")
+    lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.q_camids, s.g_pids, s.g_camids)]
+    ev = RetrievalEvaluator(s.gf.cuda(), lab[2], lab[3])
+    c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    key = [k for k in engine._CAP_MEMO if k[0] == ev._label_keys][0]
+    engine._CAP_MEMO[key] = 3                                            # stale, too small
+    c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
+    assert np.array_equal(c1, c2) and m1 == m2 and i2["cap"] == i1["cap"] and engine._CAP_MEMO[key] == i1["cap"]

@@ -144,6 +144,45 @@ def test_one_shot_c_entry_point():
     assert rc == _lib.ERR_CAPACITY
 
 
+def test_one_call_retrieval_c_entry_point():
+    """ieee_retrieve_eval: raw features + labels in, (cmc, summary, distance block) out, one C call."""
+    s = make_retrieval_set(70, 500, 12, 3, dim=96, sigma=2.0, seed=5)
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    qf, gf = s.qf.to(dev), s.gf.to(dev)
+    lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.g_pids, s.q_camids, s.g_camids)]
+    Q, G, D, K = 70, 500, 96, 10
+    nbytes = lib.ieee_retrieve_workspace_bytes(Q, G, D, 0, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dist = torch.empty((Q, 512), dtype=torch.float32, device=dev)
+    cmc = torch.empty(K, dtype=torch.float32, device=dev)
+    summ = torch.empty(64, dtype=torch.uint8, device=dev)
+    ap = torch.empty(Q, dtype=torch.float64, device=dev)
+
+    def run(cap, cap_out):
+        _lib.call("ieee_retrieve_eval", qf.data_ptr(), D, gf.data_ptr(), D, 0, Q, G, D, 0, 0, 0, lab[0].data_ptr(),
+                  lab[1].data_ptr(), lab[2].data_ptr(), lab[3].data_ptr(), K, cap, cap_out, dist.data_ptr(), 512,
+                  cmc.data_ptr(), summ.data_ptr(), ap.data_ptr(), None, ws.data_ptr(), nbytes, _lib.stream())
+        return _lib.EvalSummary.from_buffer_copy(summ.cpu().numpy().tobytes())
+
+    import ctypes
+    need = ctypes.c_int32(0)
+    res = run(0, ctypes.byref(need))                                       # sizing call: queries the capacity
+    d = dist[:, :G].cpu().numpy()
+    assert np.allclose(d, R.compute_distance_matrix(s.qf, s.gf).numpy(), rtol=1e-4, atol=1e-2)
+    cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, max_rank=K)
+    pos = R.kept_positions(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert np.array_equal(cmc.cpu().numpy(), cmc_o) and abs(res.mAP - map_o) < 1e-9 and res.status == 0
+    assert res.list_overflow == 0 and need.value >= max(p.size for p in pos)
+    assert abs(res.mINP - R.mean_inverse_negative_penalty(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)) < 1e-12
+    ap_o = np.array([((np.arange(p.size) + 1.0) / (p + 1.0)).sum() / p.size if p.size else 0.0 for p in pos])
+    assert np.abs(ap.cpu().numpy() - ap_o).max() < 1e-12
+    res2 = run(need.value, None)                                           # hinted call: asynchronous, same result
+    assert res2.mAP == res.mAP and res2.list_overflow == 0
+    res3 = run(2, None)                                                    # hint too small: flagged, not trusted
+    assert 2 < res3.list_overflow <= need.value
+
+
 @pytest.mark.parametrize("k", [1, 20, 21, 100])
 def test_topk_ranked_list(k):
     s = make_retrieval_set(60, 2500, 20, 4, dim=64, sigma=2.0, seed=k)

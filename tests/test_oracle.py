@@ -48,6 +48,20 @@ def test_counting_form_equals_sort_form(golden_dir, name):
     assert np.array_equal(cmc, g["cmc"]) and abs(mAP - float(g["mAP"])) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["rank_cython_shape.npz", "rank_clustered.npz", "rank_ties_stable.npz"])
+def test_minp_sort_form_equals_counting_form(golden_dir, name):
+    """mINP has no reference code (README.rst:45 names it only): the sort form over the reference's ranked list and
+    the counting form the kernels use (R / (position of the hardest relevant item + 1)) must agree; plus a hand case."""
+    g = load(golden_dir, name)
+    args = (g["distmat"], g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"])
+    pos = [p for p in R.kept_positions(*args) if p.size]
+    by_count = float(np.mean([p.size / (p[-1] + 1.0) for p in pos]))
+    assert abs(R.mean_inverse_negative_penalty(*args) - by_count) < 1e-12
+    # one query, kept list = [neg, POS, neg, POS, neg] -> INP = 2 / 4
+    d = np.array([[0.1, 0.2, 0.3, 0.4, 0.5]], dtype=np.float32)
+    assert R.mean_inverse_negative_penalty(d, [7], [1, 7, 2, 7, 3], [0], [1, 1, 1, 1, 1]) == 0.5
+
+
 def test_rerank_matches_golden(golden_dir):
     g = load(golden_dir, "rerank_small.npz")
     for key, kw in (("out_default", {}), ("out_small", dict(k1=6, k2=3, lambda_value=0.5)),
