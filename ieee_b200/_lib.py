@@ -43,7 +43,7 @@ SIGNATURES = {
     "ieee_rank_list_cap_sync": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(i32), vp]),
     "ieee_rank_gather": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "ieee_rank_count_smem_bytes": (sz, [i32, i32]),
-    "ieee_rank_count": (C.c_int, [vp, i64, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "ieee_rank_count": (C.c_int, [vp, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "ieee_rank_query_metrics": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
     "ieee_rank_reduce": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]),
     "ieee_rank_finalize_workspace_bytes": (sz, [i64]),

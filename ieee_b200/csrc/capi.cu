@@ -46,7 +46,7 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
                 const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel, int32_t* n_rel,
                 uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream);
 size_t rank_count_smem(int shards, int cap);
-int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
+int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream);
 size_t rank_finalize_workspace_bytes(int64_t Q);
@@ -231,11 +231,11 @@ int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, con
 size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap) { return rank_count_smem(shards, cap); }
 
 int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards, int32_t cap,
-                    const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
+                    int32_t out_cap, const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                     int32_t* counts, unsigned long long* ties, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return rank_count(distmat, ld, Q, G, g_offset, shards, cap, rel_all, n_rel, junk, n_junk, counts, ties,
+  return rank_count(distmat, ld, Q, G, g_offset, shards, cap, out_cap, rel_all, n_rel, junk, n_junk, counts, ties,
                     (cudaStream_t)stream);
 }
 
@@ -319,7 +319,7 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
   IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
-  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
+  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
   return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
 }
 
@@ -386,7 +386,7 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
-  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
+  if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
   return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, per_query_ap, per_query_first, fws, stream,
                        scratch + 1);
 }

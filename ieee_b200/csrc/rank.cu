@@ -364,6 +364,112 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Streaming body of the warp-per-query kernel.  Per element: 4 float ops to the cell index, one 16-bit table load,
+// one fire-and-forget shared atomic on the lane's private counter column (no read-modify-write dependency chain
+// between the 16 elements in flight), one mask update.  Elements whose cell holds thresholds are fixed up after
+// the batch in ONE rolled loop over the mask (the distance is re-read, an L2 hit): the hot loop stays a few hundred
+// instructions long instead of sixteen inlined copies of the exact (key, index) comparison.
+//
+// Cell word (uint16): bit 0 = the cell holds thresholds, bits 1..6 = (number of thresholds in the cell) - 1,
+// bits 7..15 = first bin of the cell * 128 = byte offset of that bin's counter row (bin R + 1 = "after every
+// threshold": a real row nobody reads, so the body needs no branch).
+// ---------------------------------------------------------------------------------------------------------
+struct WarpCount {
+  const uint64_t* T;
+  const uint16_t* cell;
+  uint8_t* col;          // this lane's counter column: *(int32_t*)(col + bin * 128)
+  const float* row;
+  float lo, scale, top;  // cell index = floor(min((d - lo) * scale + 1, top)), top = L + 1
+  uint32_t g_offset;
+  int ties;
+};
+
+__host__ __device__ __forceinline__ uint16_t warp_cell_word(int first_bin, int n) {
+  return (uint16_t)((first_bin << 7) | (n ? (((n - 1) << 1) | 1) : 0));
+}
+
+// d < lo (and -inf) -> 0 (float->unsigned conversion saturates), [lo, hi] -> 1 .. L, d >> hi, +inf and NaN -> L + 1
+// (fminf returns the non-NaN operand: NaN ranks last, like NumPy's sort).  Monotone in d.
+__device__ __forceinline__ uint32_t warp_cell_index(float d, float lo, float scale, float top) {
+  return __float2uint_rd(fminf(fmaf(d - lo, scale, 1.0f), top));
+}
+
+__device__ __forceinline__ void warp_bump(WarpCount& c, uint32_t row_off, int delta) {
+  atomicAdd(reinterpret_cast<int32_t*>(c.col + row_off), delta);   // result unused: fire and forget, nothing waits
+}
+
+__device__ __forceinline__ void warp_fix(WarpCount& c, float d, uint32_t g) {
+  const uint32_t ce = c.cell[warp_cell_index(d, c.lo, c.scale, c.top)];
+  if (!(ce & 1u)) return;
+  const int tent = (int)(ce >> 7), n = (int)((ce >> 1) & 63u) + 1;
+  const uint64_t pe = pack_key(d, g + c.g_offset);
+  const uint32_t ke = (uint32_t)(pe >> 32);
+  int b = tent, same = 0;
+  bool is_thr = false;
+  for (int j = tent; j < tent + n; ++j) {
+    const uint64_t t = c.T[j];
+    b += (t < pe);
+    same += ((uint32_t)(t >> 32) == ke);
+    is_thr |= (t == pe);
+  }
+  if (!is_thr) c.ties += same;
+  if (b != tent) {
+    warp_bump(c, (uint32_t)tent << 7, -1);
+    warp_bump(c, (uint32_t)b << 7, 1);
+  }
+}
+
+// Eight elements at a time in two phases -- all table loads first, then all counter updates -- because the
+// compiler may not move a shared load above a shared atomic it cannot prove disjoint.
+__device__ __forceinline__ void warp_visit8(WarpCount& c, const float4& u, const float4& v, uint32_t& mask) {
+  const float d[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+  uint32_t ce[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ce[e] = c.cell[warp_cell_index(d[e], c.lo, c.scale, c.top)];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    warp_bump(c, ce[e] & 0xFF80u, 1);
+    mask = mask * 2u + (ce[e] & 1u);
+  }
+}
+
+__device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane) {
+  const float* __restrict__ row = c.row;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
+  int head = (int)(((16 - (addr & 15)) & 15) >> 2);
+  if (head > G) head = G;
+  const int nvec = (G - head) >> 2;
+  const float4* rv = reinterpret_cast<const float4*>(row + head);
+  auto one = [&](int g) {
+    const float d = row[g];
+    const uint32_t ce = c.cell[warp_cell_index(d, c.lo, c.scale, c.top)];
+    warp_bump(c, ce & 0xFF80u, 1);
+    if (ce & 1u) warp_fix(c, d, (uint32_t)g);
+  };
+  for (int g = lane; g < head; g += 32) one(g);
+  int i = lane;
+  for (; i + 96 < nvec; i += 128) {          // 4 independent 16-byte loads in flight per lane
+    const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + 32), a2 = __ldcs(rv + i + 64), a3 = __ldcs(rv + i + 96);
+    uint32_t mask = 0;
+    warp_visit8(c, a0, a1, mask);
+    warp_visit8(c, a2, a3, mask);
+#pragma unroll 1
+    while (mask) {                            // rare: bit (15 - e) <-> element e = 4 * (which load) + component
+      const int bit = 31 - __clz(mask);
+      mask &= ~(1u << bit);
+      const int e = 15 - bit;
+      const int g = head + 4 * (i + (e >> 2) * 32) + (e & 3);
+      warp_fix(c, row[g], (uint32_t)g);
+    }
+  }
+  for (; i < nvec; i += 32) {
+    const int g0 = head + 4 * i;
+    one(g0); one(g0 + 1); one(g0 + 2); one(g0 + 3);
+  }
+  for (int g = head + 4 * nvec + lane; g < G; g += 32) one(g);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // count, warp-per-query variant: for short rows (G <= 64K) the per-CTA setup of rank_count_kernel (sort, cell
 // table, zeroing and folding 256 private columns, ~8000 warp instructions) costs more than streaming the row.
 // Here every warp owns one query and does its setup with warp-level primitives only (~500 instructions);
@@ -371,14 +477,15 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
 // the generic search with shared atomics on its own histogram.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWarpQ = 8;            // queries (warps) per CTA
-constexpr int kWarpRmax = 64;        // thresholds per query the private table holds
-__host__ __device__ inline int warp_smem_per_query(int rmax) {   // T[rmax] u64 | hist[rmax + 2] | cell[1024] | priv[rmax + 2][32]
-  return ((rmax * 8 + (rmax + 2) * 4 + (kLutCells + 2) * 4 + (rmax + 2) * 32 * 4) + 15) & ~15;
+constexpr int kWarpRmax = 128;       // thresholds per query the private table holds (cell words address up to 511 bins)
+// T[rmax] u64 | hist[rmax + 2] | cell[1024 + 2 (+2: keeps priv 8-byte aligned, it doubles as u64 staging)] u16 | priv[rmax + 2][32]
+__host__ __device__ inline int warp_smem_per_query(int rmax) {
+  return ((rmax * 8 + (rmax + 2) * 4 + (kLutCells + 4) * 2 + (rmax + 2) * 32 * 4) + 15) & ~15;
 }
 
 __global__ void __launch_bounds__(32 * kWarpQ)
 rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
-                       int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
+                       int out_cap, int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                        const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                        unsigned long long* __restrict__ ties_out) {
   extern __shared__ __align__(16) uint8_t ws_raw[];
@@ -386,13 +493,21 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   uint8_t* mine = ws_raw + size_t(w) * warp_smem_per_query(rmax);
   uint64_t* T = reinterpret_cast<uint64_t*>(mine);                                   // [rmax]
   int32_t* hist = reinterpret_cast<int32_t*>(mine + rmax * 8);                        // [rmax + 2]
-  uint32_t* cell = reinterpret_cast<uint32_t*>(hist + rmax + 2);                      // [1024]
-  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells + 2);                   // [rmax + 2][32]
+  uint16_t* cell = reinterpret_cast<uint16_t*>(hist + rmax + 2);                      // [1024 + 2]
+  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells + 4);                   // [rmax + 2][32]
   const int64_t q = (int64_t)blockIdx.x * kWarpQ + w;
   if (q >= Q) return;
-  const int stride = shards * cap + 2;
+  const int stride = out_cap + 2;
   int32_t* out = counts + q * stride;
   const int nj = n_junk[q];
+  int Rtot = 0;
+  for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
+  if (lane == 0) {
+    out[stride - 1] = nj; out[stride - 2] = n_rel[q];
+    // longest merged list seen: sizes the next call's rows (out_cap); a list longer than this call's is flagged by it
+    if (ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
+  }
+  if (Rtot == 0 || Rtot > rmax) return;     // invalid query (rank.py:142-144) / row too small: caller re-runs
   // thresholds of all shards, staged in `priv` (not live yet)
   uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
   int R = 0;
@@ -402,8 +517,6 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int i = lane; i < n; i += 32) Tin[R + i] = src[i];
     R += n;
   }
-  if (lane == 0) { out[stride - 1] = nj; out[stride - 2] = n_rel[q]; }
-  if (R == 0) return;                       // invalid query (rank.py:142-144)
   __syncwarp();
   // rank sort (keys are distinct)
   for (int k = lane; k < R; k += 32) {
@@ -412,43 +525,55 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
     T[pos] = me;
   }
-  for (int i = lane; i < lut_cells_for(G) + 2; i += 32) cell[i] = 0;
   __syncwarp();
-  for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
   for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;     // own column only: i % 32 == lane
   const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
   const int L = lut_cells_for(G);
-  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
+  bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
+  // (hi - lo) * scale = L - 0.5: every threshold lands in cells 1 .. L and the map stays monotone (the -0.5 margin
+  // dwarfs fp32 rounding); everything else falls into the guard cells 0 and L + 1
   const float scale = use_lut ? ((float)L - 0.5f) / span : 0.f;
+  const float top = (float)(L + 1);
   if (use_lut) {
+    // cell of every (sorted) threshold: non-decreasing in k; kept in `hist` (not live yet) as the search array
+    uint16_t* tcell = reinterpret_cast<uint16_t*>(hist);
     for (int k = lane; k < R; k += 32) {
-      const float d = key_to_float((uint32_t)(T[k] >> 32));
-      atomicAdd(&cell[1 + min(__float2int_rd((d - lo) * scale), L - 1)], 1u << 20);
+      const uint32_t ci = warp_cell_index(key_to_float((uint32_t)(T[k] >> 32)), lo, scale, top);
+      tcell[k] = (uint16_t)min(max(ci, 1u), (uint32_t)L);
     }
     __syncwarp();
-    // exclusive scan over the 1024 cells, 32 at a time (lane <-> cell: conflict-free), carry in a register
-    int carry = 0;
-    for (int k0 = 1; k0 <= L; k0 += 32) {
-      const int cnt = (int)(cell[k0 + lane] >> 20);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-      cell[k0 + lane] = (uint32_t)(carry + incl - cnt) | ((uint32_t)cnt << 20);
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+    bool crowded = false;                     // a cell word counts at most 64 thresholds
+    for (int i = lane; i <= L + 1; i += 32) {
+      int a = 0, e = R;                       // first k with tcell[k] >= i  =  number of thresholds in earlier cells
+      while (a < e) { const int m = (a + e) >> 1; if ((int)tcell[m] < i) a = m + 1; else e = m; }
+      int n = 0;
+      while (a + n < R && (int)tcell[a + n] == i) ++n;
+      crowded |= n > 64;
+      cell[i] = (i == L + 1) ? warp_cell_word(R + 1, 0) : warp_cell_word(a, min(n, 64));
     }
-    if (lane == 0) { cell[0] = 0; cell[L + 1] = (uint32_t)(R + 1); }   // guards: bin 0 / trash bin
+    if (__any_sync(0xffffffffu, crowded)) use_lut = false;     // (generic search path below)
+    __syncwarp();
   }
+  for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
   __syncwarp();
-  CountCtx c;
-  c.T = T; c.cell = cell; c.hist = hist; c.priv = priv + lane;
-  c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
-  c.g_offset = (uint32_t)g_offset; c.ties = 0;
   const float* row = distmat + q * ld;
-  if (use_lut) count_stream<COUNT_LUT_PRIVATE, 32>(c, row, G, lane);
-  else count_stream<COUNT_SEARCH_ATOMIC, 32>(c, row, G, lane);
-  int tie_local = c.ties;
+  int tie_local = 0;
+  if (use_lut) {
+    WarpCount c;
+    c.T = T; c.cell = cell; c.col = reinterpret_cast<uint8_t*>(priv + lane); c.row = row;
+    c.lo = lo; c.scale = scale; c.top = top; c.g_offset = (uint32_t)g_offset; c.ties = 0;
+    warp_count_stream(c, G, lane);
+    tie_local = c.ties;
+  } else {
+    CountCtx c;
+    c.T = T; c.cell = nullptr; c.hist = hist; c.priv = priv + lane;
+    c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
+    c.g_offset = (uint32_t)g_offset; c.ties = 0;
+    count_stream<COUNT_SEARCH_ATOMIC, 32>(c, row, G, lane);
+    tie_local = c.ties;
+  }
   __syncwarp();
   if (use_lut) {   // fold: lane l sums bins l and l + 32 over the 32 private columns (rotated reads: conflict-free)
     for (int b = lane; b <= R; b += 32) {
@@ -489,7 +614,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
 
 __global__ void __launch_bounds__(kCountThreads, 6)
 rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
-                  int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
+                  int out_cap, int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                   const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                   unsigned long long* __restrict__ ties_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
@@ -501,8 +626,15 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   int32_t* priv = reinterpret_cast<int32_t*>(cs_raw + plan.priv_off);    // [bins][kCountThreads]
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int stride = shards * cap + 2;
+  const int stride = out_cap + 2;
   int32_t* out = counts + q * stride;
+  int Rtot = 0;
+  for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
+  if (tid == 0 && ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
+  if (Rtot > out_cap) {                      // row too small for this query's merged list: flagged above, caller re-runs
+    if (tid == 0) { out[stride - 1] = n_junk[q]; out[stride - 2] = n_rel[q]; }
+    return;
+  }
 
   // ---- thresholds: union of the shards' relevant lists -------------------------------------------------
   if (tid == 0) { misc[0] = 0; misc[1] = 0; }
@@ -650,18 +782,30 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   if (tid == 0 && ties_out != nullptr && misc[1] != 0) atomicAdd(ties_out, (unsigned long long)(long long)misc[1]);
 }
 
-int g_count_warp_max_g = 65536;   // rows up to this length use the warp-per-query kernel (ieee_set_debug_flags bit 4: off)
+// rows up to this length use the warp-per-query kernel (ieee_set_debug_flags bit 4: off; tuning override:
+// IEEE_B200_COUNT_WARP_MAX_G)
+static int count_warp_max_g() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IEEE_B200_COUNT_WARP_MAX_G");
+    v = e ? atoi(e) : 65536;
+    if (v < 0) v = 65536;
+  }
+  return v;
+}
 
 size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(max(shards * cap, 2))).total; }
 
-int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap,
+int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream) {
   IEEE_REQUIRE(distmat && rel_all && n_rel && junk && n_junk && counts, "rank_count: null pointer");
-  IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1, "rank_count: bad shape");
+  IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1 && out_cap >= 0,
+               "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
-  if (G <= g_count_warp_max_g && shards * cap <= kWarpRmax && !(g_debug_flags & 16)) {     // short rows: one warp per query
-    const int rmax = (shards * cap + 1) & ~1;      // even: keeps the 8-byte alignment of every query's T
+  if (out_cap == 0 || out_cap > shards * cap) out_cap = shards * cap;       // a merged list cannot be longer than this
+  if (G <= count_warp_max_g() && out_cap <= kWarpRmax && !(g_debug_flags & 16)) {     // short rows: one warp per query
+    const int rmax = (out_cap + 1) & ~1;           // even: keeps the 8-byte alignment of every query's T
     const size_t wsmem = size_t(kWarpQ) * warp_smem_per_query(rmax);
     static size_t wattr = 0;
     if (wsmem > 48 * 1024 && wsmem > wattr) {
@@ -669,21 +813,20 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
       wattr = wsmem;
     }
     rank_count_warp_kernel<<<(unsigned)((Q + kWarpQ - 1) / kWarpQ), 32 * kWarpQ, wsmem, stream>>>(
-        distmat, ld, Q, (int)G, g_offset, shards, cap, rmax, rel_all, n_rel, junk, n_junk, counts, ties);
+        distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel, junk, n_junk, counts, ties);
     count_launch();
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
   }
-  const int Rp = next_pow2(max(shards * cap, 2));
+  const int Rp = next_pow2(max(out_cap, 2));
   const size_t smem = count_smem_plan(Rp).total;
-  IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: shards*cap=%d relevant items per query exceed the shared-memory budget",
-               shards * cap);
+  IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: %d relevant items per query exceed the shared-memory budget", out_cap);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, Rp, rel_all,
+  rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, Rp, rel_all,
                                                                   n_rel, junk, n_junk, counts, ties);
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());

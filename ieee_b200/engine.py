@@ -11,6 +11,7 @@ all-reduced, and every rank ends with the same (cmc, mAP) the single-GPU path pr
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -63,15 +64,15 @@ _CAP_MEMO = {}
 _STAGE_POOL = {}
 
 
-def _stages_for(Qb, cap, world, device):
+def _stages_for(Qb, cap, world, device, width=0):
     """Stage buffers are reused across evaluations of the same shape (all work on them is ordered by the compute
     stream); creating the dozen small tensors costs more host time than the kernels take to launch."""
-    key = (Qb, cap, world, str(device))
+    key = (Qb, cap, world, str(device), width)
     st = _STAGE_POOL.get(key)
     if st is None:
         if len(_STAGE_POOL) > 8:
             _STAGE_POOL.clear()
-        st = _STAGE_POOL[key] = RankStages(Qb, cap, world, device)
+        st = _STAGE_POOL[key] = RankStages(Qb, cap, world, device, width)
     return st
 
 
@@ -169,9 +170,9 @@ class RetrievalEvaluator:
         rows = max(128, int(self.block_bytes // (4 * max(self.G, 1))) // 128 * 128)
         return min(Q, rows)
 
-    def _rank_block(self, dist, qp, qc, cap, ap, first, short, ties, inp):
+    def _rank_block(self, dist, qp, qc, cap, width, ap, first, short, ties, inp):
         Qb = dist.shape[0]
-        st = _stages_for(Qb, cap, self.world, self.device)
+        st = _stages_for(Qb, cap, self.world, self.device, width)
         torch.cuda.current_stream().wait_event(self.labels.ready)
         st.gather(dist, qp, qc, self.labels, self.g_offset)
         if self.world > 1:
@@ -185,7 +186,8 @@ class RetrievalEvaluator:
             st.count(dist, self.G, self.g_offset)
         ties[0:1] += st.flags[1:2]
         ties[1:2] += st.flags[0:1] & 0xFFFFFFFF      # gather's overflow word (needed capacity, 0 = all lists fitted)
-        _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, self.world, cap, self.max_rank,
+        torch.maximum(ties[2:3], st.flags[2:3], out=ties[2:3])      # longest merged list (sizes the next call's rows)
+        _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, 1, st.width, self.max_rank,
                   ap.data_ptr(), first.data_ptr(), short.data_ptr(), inp.data_ptr(), _lib.stream())
         return st
 
@@ -228,7 +230,7 @@ class RetrievalEvaluator:
             memo_key = None
             if use_cap_memo and self._label_keys[0] is not None and _tensor_key(q_pids) is not None:
                 memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
-            cap = _CAP_MEMO.get(memo_key, 0) if memo_key is not None else 0
+            cap = _CAP_MEMO.get(memo_key, (0, 0))[0] if memo_key is not None else 0
             cur = torch.cuda.current_stream()
             cur.wait_event(self.labels.ready)
             if cap <= 0:
@@ -237,7 +239,7 @@ class RetrievalEvaluator:
                 if memo_key is not None:
                     if len(_CAP_MEMO) > 64:
                         _CAP_MEMO.clear()
-                    _CAP_MEMO[memo_key] = cap
+                    _CAP_MEMO[memo_key] = (cap, 0)
             k_eff = min(self.max_rank, self.g_total)
             prec = _lib.PRECISIONS[self.precision]
             ws, res, res_off, res_host = _fused_buffers(Q, D, prec, cap, k_eff, self.device)
@@ -268,9 +270,11 @@ class RetrievalEvaluator:
         return cmc_host, float(summary.mAP), info
 
     def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False, use_cap_memo: bool = True,
-                 one_call: bool = True):
+                 one_call: bool | None = None):
         """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
         `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
+        if one_call is None:
+            one_call = os.environ.get("IEEE_B200_ONE_CALL", "1") != "0"
         if (one_call and self.world == 1 and qf.is_cuda and self._host_gallery is None and len(self.chunks) == 1
                 and isinstance(self.chunks[0][1], PackedFeatures) and 0 < qf.shape[0] <= self._block_rows(qf.shape[0])
                 and qf.dtype in _lib.DTYPES):
@@ -319,7 +323,7 @@ class RetrievalEvaluator:
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
             inp = torch.empty(Q, dtype=torch.float64, device=self.device)
-            ties = torch.zeros(2, dtype=torch.int64, device=self.device)        # [tie pairs, list overflow]
+            ties = torch.zeros(3, dtype=torch.int64, device=self.device)        # [tie pairs, list overflow, longest merged list]
             rows = self._block_rows(Q)
             if self._block is None or self._block.shape[0] < rows:
                 # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
@@ -348,7 +352,7 @@ class RetrievalEvaluator:
             memo_key = None
             if use_cap_memo and self._label_keys[0] is not None and _tensor_key(q_pids) is not None:
                 memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
-            cap = _CAP_MEMO.get(memo_key) if memo_key is not None else None
+            cap, width = _CAP_MEMO.get(memo_key, (None, 0)) if memo_key is not None else (None, 0)
             if cap is not None:
                 dist = contraction(0, min(Q, rows))
                 TRACE.mark("contraction(block 0) queued (capacity memo hit)")
@@ -368,21 +372,17 @@ class RetrievalEvaluator:
                     cap_t = torch.tensor([cap], dtype=torch.int32, device=self.device)
                     dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
                     cap = int(cap_t.item())
-                if memo_key is not None:
-                    if len(_CAP_MEMO) > 64:
-                        _CAP_MEMO.clear()
-                    _CAP_MEMO[memo_key] = cap
             full = None
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)
                 if s > 0:
                     dist = contraction(s, e)
-                self._rank_block(dist, qp[s:e], qc[s:e], cap, ap[s:e], first[s:e], short[s:e], ties, inp[s:e])
+                self._rank_block(dist, qp[s:e], qc[s:e], cap, width, ap[s:e], first[s:e], short[s:e], ties, inp[s:e])
                 if return_distmat:
                     full = dist.clone() if full is None else torch.cat([full, dist], 0)
             if self.world > 1:
                 import torch.distributed as dist_
-                dist_.all_reduce(ties, group=self.group)
+                dist_.all_reduce(ties[:2], group=self.group)      # [2] (longest merged list) is the same on every rank
             k_eff = min(self.max_rank, self.g_total)
             cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
             summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
@@ -390,12 +390,19 @@ class RetrievalEvaluator:
             _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
                       cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
-            out = torch.cat([cmc.view(torch.uint8), summ, ties[1:2].view(torch.uint8)]).cpu().numpy()   # one D2H copy, synchronises
+            out = torch.cat([cmc.view(torch.uint8), summ, ties[1:3].view(torch.uint8)]).cpu().numpy()   # one D2H copy, synchronises
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
             summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff: 4 * k_eff + 64].tobytes())
-            overflow = int(out[4 * k_eff + 64:].view(np.int64)[0])
+            overflow, longest = (int(v) for v in out[4 * k_eff + 64:].view(np.int64)[:2])
+            overflow = overflow or (longest > (width if width > 0 else self.world * cap))   # rows narrower than a merged list
+            if memo_key is not None and not overflow:
+                if len(_CAP_MEMO) > 64:
+                    _CAP_MEMO.clear()
+                _CAP_MEMO[memo_key] = (cap, max(longest, 1))
         if overflow:
             # a list did not fit the (memoised) capacity: forget the hint and run again with the exact value
+            if not use_cap_memo:
+                raise RuntimeError("ieee_b200: per-query lists overflowed an exactly sized buffer (cap=%d, longest=%d)" % (cap, longest))
             _CAP_MEMO.pop(memo_key, None)
             return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False, one_call=one_call)
         TRACE.report()

@@ -92,14 +92,18 @@ class GalleryLabels:
 class RankStages:
     """The three stream-ordered stages of include/ieee_b200.h (gather / count / finalize) over torch buffers."""
 
-    def __init__(self, Q: int, cap: int, shards: int, device):
+    def __init__(self, Q: int, cap: int, shards: int, device, width: int = 0):
+        """width: row width of the count table = longest merged (all-shard) relevant list to expect; 0 = shards * cap,
+        which always fits.  flags[2] reports the longest list actually seen (see ieee_rank_count)."""
         self.Q, self.cap, self.shards, self.device = Q, cap, shards, device
+        self.width = shards * cap if width <= 0 else min(width, shards * cap)
         self.rel = torch.empty((Q, cap + 1), dtype=torch.int64, device=device)  # uint64 keys; [:, cap] = list length
         self.junk = torch.empty((Q, cap), dtype=torch.int64, device=device)
         self.n_rel = torch.empty(Q, dtype=torch.int32, device=device)
         self.n_junk = torch.empty(Q, dtype=torch.int32, device=device)
-        self.counts = torch.empty((Q, shards * cap + 2), dtype=torch.int32, device=device)
-        self.flags = torch.zeros(8, dtype=torch.int64, device=device)          # [0] overflow (int32), [1] ties (uint64)
+        self.counts = torch.empty((Q, self.width + 2), dtype=torch.int32, device=device)
+        # [0] gather overflow (int32), [1] tie pairs (uint64), [2] longest merged list (uint64)
+        self.flags = torch.zeros(8, dtype=torch.int64, device=device)
         self.cmc = None
         self.summary = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=device)
         self.ap = torch.empty(Q, dtype=torch.float64, device=device)
@@ -117,7 +121,7 @@ class RankStages:
         """rel_all: the all-gathered relevant lists [shards, Q, cap + 1] (this rank's own list on one GPU)."""
         rel_all = self.rel if rel_all is None else rel_all
         _lib.call("ieee_rank_count", distmat.data_ptr(), distmat.stride(0), self.Q, G, g_offset, self.shards, self.cap,
-                  rel_all.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
+                  self.width, rel_all.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
                   self.counts.data_ptr(), self.flags.data_ptr() + 8, _lib.stream())
 
     def finalize(self, G_total: int, max_rank: int, counts=None, ties=None):
@@ -126,7 +130,7 @@ class RankStages:
         k_eff = min(max_rank, G_total)
         self.cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
         ties_ptr = self.flags.data_ptr() + 8 if ties is None else ties.data_ptr()
-        _lib.call("ieee_rank_finalize", counts.data_ptr(), self.Q, G_total, self.shards, self.cap, max_rank, ties_ptr,
+        _lib.call("ieee_rank_finalize", counts.data_ptr(), self.Q, G_total, 1, self.width, max_rank, ties_ptr,
                   self.cmc.data_ptr(), self.summary.data_ptr(), self.ap.data_ptr(), self.first.data_ptr(),
                   self.ws.data_ptr(), _lib.stream())
 

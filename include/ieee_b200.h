@@ -158,14 +158,19 @@ int ieee_rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, con
 /* count: thresholds of query q = union over the `shards` relevant lists rel_all[s][q][cap + 1] (the all-gathered
  * buffers; shards = 1 and rel_all = rel on one GPU).  Streams the local distance row once and writes
  * counts[q, k] = #{local kept g : (d, g) <lex T_k} for the k-th smallest threshold, k < R[q] (= lengths summed over
- * shards), plus counts[q, shards*cap] = this shard's number of relevant items (n_rel) and
- * counts[q, shards*cap + 1] = its number of junk items.  counts is int32[Q, shards*cap + 2]; it is summed over
- * shards by the caller (all-reduce) before query_metrics / finalize, which read R[q] from it.
- * ties (uint64[1], may be NULL) accumulates bit-equal (threshold, other kept item) pairs. */
+ * shards), plus counts[q, W] = this shard's number of relevant items (n_rel) and counts[q, W + 1] = its number of
+ * junk items.  counts is int32[Q, W + 2] with row width W = out_cap (0: W = shards*cap, always enough); it is
+ * summed over shards by the caller (all-reduce) before query_metrics / finalize, which read R[q] from it -- call
+ * those with shards = 1, cap = W.  A merged list is rarely as long as shards*cap: passing the longest one seen
+ * before (stats[1] of an earlier call with the same labels) as out_cap shrinks the all-reduce by ~the shard count.
+ * stats (uint64[2], may be NULL): [0] accumulates bit-equal (threshold, other kept item) pairs, [1] receives the
+ * longest merged list (max-updated).  stats[1] > out_cap means some rows were too narrow and their counts were
+ * NOT written: run again with out_cap >= stats[1]. */
 size_t ieee_rank_count_smem_bytes(int32_t shards, int32_t cap);
 int ieee_rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int32_t shards,
-                    int32_t cap, const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk,
-                    const int32_t* n_junk, int32_t* counts, unsigned long long* ties, ieee_stream_t stream);
+                    int32_t cap, int32_t out_cap, const uint64_t* rel_all, const int32_t* n_rel,
+                    const uint64_t* junk, const int32_t* n_junk, int32_t* counts, unsigned long long* stats,
+                    ieee_stream_t stream);
 
 /* finalize = ieee_rank_query_metrics (per query) followed by ieee_rank_reduce (over queries); the two halves
  * are exported separately so that query blocks can share one final reduction.

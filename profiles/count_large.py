@@ -9,7 +9,7 @@ from ieee_b200.engine import PackedFeatures, packed_distmat
 from ieee_b200.metrics.rank import GalleryLabels, RankStages
 from ieee_b200.testing import make_retrieval_set
 
-Q, G = 2048, 125000
+Q, G = (int(sys.argv[1]) if len(sys.argv) > 1 else 8192), 125000
 s = make_retrieval_set(Q, G, 12500, 8, dim=256, sigma=2.0, seed=3)
 dev = torch.device("cuda")
 q, g = PackedFeatures(s.qf.to(dev), "euclidean", False, "f16x3"), PackedFeatures(s.gf.to(dev), "euclidean", False, "f16x3")

@@ -75,12 +75,21 @@ def test_capacity_memo_is_checked_not_trusted(one_call):
     ev = RetrievalEvaluator(s.gf.cuda(), lab[2], lab[3])
     c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)
     key = [k for k in engine._CAP_MEMO if k[0] == ev._label_keys][0]
-    assert engine._CAP_MEMO[key] == i1["cap"]
+    assert engine._CAP_MEMO[key][0] == i1["cap"]
     c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)              # memo hit: same result, no capacity query
     assert np.array_equal(c1, c2) and m1 == m2
-    engine._CAP_MEMO[key] = 2                                            # poison the hint: far too small
+    engine._CAP_MEMO[key] = (2, 0)                                       # poison the hint: far too small
     c3, m3, i3 = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=one_call)
     assert np.array_equal(c1, c3) and m1 == m3 and i3["cap"] == i1["cap"]
+    if not one_call:
+        # the staged path also remembers the longest merged list (row width of the count table); too narrow a
+        # hint is reported by the count kernel and the evaluation is redone
+        ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=False)
+        cap, width = engine._CAP_MEMO[key]
+        assert 1 <= width <= cap
+        engine._CAP_MEMO[key] = (cap, 1)
+        c4, m4, _ = ev.evaluate(s.qf.cuda(), lab[0], lab[1], one_call=False)
+        assert np.array_equal(c1, c4) and m1 == m4
     lab[0][0] += 0                                                       # in-place op bumps the version: key changes
     assert engine._tensor_key(lab[0]) != key[1]
 
@@ -110,6 +119,6 @@ def test_one_call_path_checks_the_capacity_hint():
     ev = RetrievalEvaluator(s.gf.cuda(), lab[2], lab[3])
     c1, m1, i1 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
     key = [k for k in engine._CAP_MEMO if k[0] == ev._label_keys][0]
-    engine._CAP_MEMO[key] = 3                                            # stale, too small
+    engine._CAP_MEMO[key] = (3, 0)                                       # stale, too small
     c2, m2, i2 = ev.evaluate(s.qf.cuda(), lab[0], lab[1])
-    assert np.array_equal(c1, c2) and m1 == m2 and i2["cap"] == i1["cap"] and engine._CAP_MEMO[key] == i1["cap"]
+    assert np.array_equal(c1, c2) and m1 == m2 and i2["cap"] == i1["cap"] and engine._CAP_MEMO[key][0] == i1["cap"]

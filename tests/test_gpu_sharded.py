@@ -33,19 +33,33 @@ def test_shard_stages_on_one_gpu(shards):
         dl = torch.from_numpy(np.ascontiguousarray(d[:, g0:g1])).to(dev)
         parts.append((g0, g1, dl, GalleryLabels(s.g_pids[g0:g1], s.g_camids[g0:g1], dev)))
     cap = max(p[3].list_cap(qp) for p in parts)
-    stages = [RankStages(Q, cap, shards, dev) for _ in parts]
-    for st, (g0, g1, dl, gal) in zip(stages, parts):
-        st.gather(dl, qp, qc, gal, g0)
-    rel_all = torch.stack([st.rel for st in stages]).contiguous()          # what the all-gather produces
-    for st, (g0, g1, dl, gal) in zip(stages, parts):
-        st.count(dl, g1 - g0, g0, rel_all)
-    total = torch.stack([st.counts for st in stages]).sum(0).to(torch.int32).contiguous()
-    ties = torch.stack([st.flags[1:2] for st in stages]).sum(0).contiguous()
-    fin = stages[0]
-    fin.finalize(G, 20, counts=total, ties=ties)
-    summary = fin.read_summary()
+
+    def run(width):
+        stages = [RankStages(Q, cap, shards, dev, width) for _ in parts]
+        for st, (g0, g1, dl, gal) in zip(stages, parts):
+            st.gather(dl, qp, qc, gal, g0)
+        rel_all = torch.stack([st.rel for st in stages]).contiguous()          # what the all-gather produces
+        for st, (g0, g1, dl, gal) in zip(stages, parts):
+            st.count(dl, g1 - g0, g0, rel_all)
+        total = torch.stack([st.counts for st in stages]).sum(0).to(torch.int32).contiguous()
+        ties = torch.stack([st.flags[1:2] for st in stages]).sum(0).contiguous()
+        longest = int(torch.stack([st.flags[2] for st in stages]).max().item())
+        fin = stages[0]
+        fin.finalize(G, 20, counts=total, ties=ties)
+        return fin, fin.read_summary(), longest
+
+    fin, summary, longest = run(0)                                           # rows as wide as shards * cap
     assert np.array_equal(fin.cmc.cpu().numpy(), cmc_o) and abs(summary.mAP - map_o) < 1e-9
     assert np.array_equal(fin.first.cpu().numpy(), info["first_hit"])
+    pos = R.kept_positions(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert longest == max(p.size for p in pos) <= shards * cap
+    fin2, summary2, longest2 = run(longest)                                  # rows as wide as the longest merged list
+    assert longest2 == longest and fin2.counts.shape[1] == longest + 2
+    assert np.array_equal(fin2.cmc.cpu().numpy(), cmc_o) and summary2.mAP == summary.mAP
+    assert np.array_equal(fin2.first.cpu().numpy(), info["first_hit"])
+    if longest > 1:
+        _, _, longest3 = run(longest - 1)                                    # too narrow: reported, never silent
+        assert longest3 == longest
 
 
 def test_topk_merge_across_shards():
