@@ -335,8 +335,16 @@ __device__ __forceinline__ void count_stream(CountCtx& c, const float* __restric
   if (head > G) head = G;
   const int nvec = (G - head) >> 2;
   const float4* rv = reinterpret_cast<const float4*>(row + head);
-  if constexpr (MODE == COUNT_SEARCH_ATOMIC) {
-    for (int g = tid; g < G; g += NT) count_visit_search<NT>(c, row[g], (uint32_t)g);
+  if constexpr (MODE == COUNT_SEARCH_ATOMIC) {      // non-finite thresholds only; still keep four loads in flight
+    int g = tid;
+    for (; g + 3 * NT < G; g += 4 * NT) {
+      const float d0 = row[g], d1 = row[g + NT], d2 = row[g + 2 * NT], d3 = row[g + 3 * NT];
+      count_visit_search<NT>(c, d0, (uint32_t)g);
+      count_visit_search<NT>(c, d1, (uint32_t)(g + NT));
+      count_visit_search<NT>(c, d2, (uint32_t)(g + 2 * NT));
+      count_visit_search<NT>(c, d3, (uint32_t)(g + 3 * NT));
+    }
+    for (; g < G; g += NT) count_visit_search<NT>(c, row[g], (uint32_t)g);
     return;
   } else {
     auto one = [&](float d, uint32_t g) { if (count_visit<MODE, NT>(c, d)) count_fix<MODE, NT>(c, d, g); };
@@ -406,6 +414,7 @@ __device__ __forceinline__ void warp_fix(WarpCount& c, float d, uint32_t g) {
   const uint32_t ke = (uint32_t)(pe >> 32);
   int b = tent, same = 0;
   bool is_thr = false;
+#pragma unroll 1                          // rare, divergent code: keep it small (n is 1 nearly always)
   for (int j = tent; j < tent + n; ++j) {
     const uint64_t t = c.T[j];
     b += (t < pe);
@@ -449,7 +458,8 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane)
   for (int g = lane; g < head; g += 32) one(g);
   int i = lane;
   for (; i + 96 < nvec; i += 128) {          // 4 independent 16-byte loads in flight per lane
-    const float4 a0 = __ldcs(rv + i), a1 = __ldcs(rv + i + 32), a2 = __ldcs(rv + i + 64), a3 = __ldcs(rv + i + 96);
+    // plain (L1-allocating) loads: the rare exact pass below re-reads a distance, and finds it in L1
+    const float4 a0 = __ldg(rv + i), a1 = __ldg(rv + i + 32), a2 = __ldg(rv + i + 64), a3 = __ldg(rv + i + 96);
     uint32_t mask = 0;
     warp_visit8(c, a0, a1, mask);
     warp_visit8(c, a2, a3, mask);
@@ -459,7 +469,7 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane)
       mask &= ~(1u << bit);
       const int e = 15 - bit;
       const int g = head + 4 * (i + (e >> 2) * 32) + (e & 3);
-      warp_fix(c, row[g], (uint32_t)g);
+      warp_fix(c, __ldg(row + g), (uint32_t)g);
     }
   }
   for (; i < nvec; i += 32) {
@@ -531,10 +541,12 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
   const int L = lut_cells_for(G);
-  bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f && isfinite((float)kLutCells / span);
+  bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi);
   // (hi - lo) * scale = L - 0.5: every threshold lands in cells 1 .. L and the map stays monotone (the -0.5 margin
-  // dwarfs fp32 rounding); everything else falls into the guard cells 0 and L + 1
-  const float scale = use_lut ? ((float)L - 0.5f) / span : 0.f;
+  // dwarfs fp32 rounding); everything else falls into the guard cells 0 and L + 1.  Any finite positive scale is
+  // CORRECT (cells only pre-sort, occupied cells compare exactly), so a single threshold or a tiny span (scale
+  // would overflow) just clamps it: d == lo -> cell 1, anything above -> beyond the table.
+  const float scale = use_lut ? fminf(((float)L - 0.5f) / span, 1.2676506e30f /* 2^100 */) : 0.f;
   const float top = (float)(L + 1);
   if (use_lut) {
     // cell of every (sorted) threshold: non-decreasing in k; kept in `hist` (not live yet) as the search array
@@ -544,14 +556,40 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
       tcell[k] = (uint16_t)min(max(ci, 1u), (uint32_t)L);
     }
     __syncwarp();
+    // Cell words in three warp-wide steps (O(L / 32) per lane, no per-cell search):
+    //   1. clear the table; 2. the first threshold of every run of equal cells writes that cell's word
+    //   (first bin = its rank k, count = run length; bit 0 marks the cell as occupied); 3. every empty cell
+    //   inherits "first bin" = a + n of the nearest occupied cell below it: each lane owns a contiguous chunk of
+    //   cells, finds the last occupied one, the warp passes those values upwards, and a second walk fills in.
+    uint32_t* cell32 = reinterpret_cast<uint32_t*>(cell);
+    for (int i = lane; i < (L + 4) / 2; i += 32) cell32[i] = 0;
+    __syncwarp();
     bool crowded = false;                     // a cell word counts at most 64 thresholds
-    for (int i = lane; i <= L + 1; i += 32) {
-      int a = 0, e = R;                       // first k with tcell[k] >= i  =  number of thresholds in earlier cells
-      while (a < e) { const int m = (a + e) >> 1; if ((int)tcell[m] < i) a = m + 1; else e = m; }
-      int n = 0;
-      while (a + n < R && (int)tcell[a + n] == i) ++n;
-      crowded |= n > 64;
-      cell[i] = (i == L + 1) ? warp_cell_word(R + 1, 0) : warp_cell_word(a, min(n, 64));
+    for (int k = lane; k < R; k += 32) {
+      const int cidx = tcell[k];
+      if (k == 0 || (int)tcell[k - 1] != cidx) {
+        int n = 1;
+        while (k + n < R && (int)tcell[k + n] == cidx) ++n;
+        crowded |= n > 64;
+        cell[cidx] = warp_cell_word(k, min(n, 64));
+      }
+    }
+    __syncwarp();
+    const int chunk = (L + 2 + 31) / 32;
+    const int c0 = lane * chunk, c1 = min(c0 + chunk, L + 2);
+    int last = -1;                            // first bin that follows this lane's last occupied cell
+    for (int i = c0; i < c1; ++i) {
+      const uint32_t w = cell[i];
+      if (w & 1u) last = (int)(w >> 7) + (int)((w >> 1) & 63u) + 1;
+    }
+    const uint32_t have = __ballot_sync(0xffffffffu, last >= 0) & ((1u << lane) - 1u);
+    const int src = have ? 31 - __clz(have) : lane;
+    const int below = __shfl_sync(0xffffffffu, last, src);
+    int run = have ? below : 0;
+    for (int i = c0; i < c1; ++i) {
+      const uint32_t w = cell[i];
+      if (w & 1u) run = (int)(w >> 7) + (int)((w >> 1) & 63u) + 1;
+      else cell[i] = (i == L + 1) ? warp_cell_word(R + 1, 0) : warp_cell_word(run, 0);
     }
     if (__any_sync(0xffffffffu, crowded)) use_lut = false;     // (generic search path below)
     __syncwarp();
@@ -684,11 +722,11 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   const float lo = key_to_float(kmin), hi = key_to_float(kmax);
   const float span = hi - lo;
   const int L = lut_cells_for(G);
-  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && span > 0.f &&
-                       isfinite((float)kLutCells / span) && R < (1 << 11);
+  const bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi) && R < (1 << 11);
   // (hi - lo) * scale = L - 0.5: every in-range distance lands in cells [0, L) and the map stays monotone (the -0.5
-  // margin dwarfs fp32 rounding); out-of-range elements fall into the guard cells
-  const float scale = use_lut ? ((float)L - 0.5f) / span : 0.f;
+  // margin dwarfs fp32 rounding); out-of-range elements fall into the guard cells.  Clamped for a single threshold /
+  // tiny span (any finite positive scale is correct: occupied cells compare exactly).
+  const float scale = use_lut ? fminf(((float)L - 0.5f) / span, 1.2676506e30f /* 2^100 */) : 0.f;
   if (use_lut) {
     for (int k = tid; k < R; k += kCountThreads) {
       const float d = key_to_float((uint32_t)(T[k] >> 32));

@@ -175,13 +175,17 @@ class RetrievalEvaluator:
         st = _stages_for(Qb, cap, self.world, self.device, width)
         torch.cuda.current_stream().wait_event(self.labels.ready)
         st.gather(dist, qp, qc, self.labels, self.g_offset)
+        TRACE.mark("  gather")
         if self.world > 1:
             import torch.distributed as dist_
             # the lists carry their own lengths (last column): one all-gather, then one all-reduce of the counts
             rel_all = torch.empty((self.world, Qb, cap + 1), dtype=torch.int64, device=self.device)
             dist_.all_gather_into_tensor(rel_all, st.rel, group=self.group)
+            TRACE.mark("  all-gather of relevant lists")
             st.count(dist, self.G, self.g_offset, rel_all)
+            TRACE.mark("  count")
             dist_.all_reduce(st.counts, group=self.group)
+            TRACE.mark("  all-reduce of counts")
         else:
             st.count(dist, self.G, self.g_offset)
         ties[0:1] += st.flags[1:2]
@@ -189,6 +193,7 @@ class RetrievalEvaluator:
         torch.maximum(ties[2:3], st.flags[2:3], out=ties[2:3])      # longest merged list (sizes the next call's rows)
         _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, 1, st.width, self.max_rank,
                   ap.data_ptr(), first.data_ptr(), short.data_ptr(), inp.data_ptr(), _lib.stream())
+        TRACE.mark("  query metrics")
         return st
 
     @classmethod

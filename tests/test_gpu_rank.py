@@ -91,6 +91,38 @@ def test_heavy_ties_and_special_values():
     check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
 
 
+@pytest.mark.parametrize("G", [700, 70000])        # warp-per-query kernel / CTA-per-query kernel
+def test_degenerate_threshold_spans(G):
+    """One relevant item per query, two at the same distance, two one ulp apart, a huge span: the cell table must
+    stay exact when (d_max - d_min) of the relevant items is 0, tiny or enormous."""
+    rng = np.random.RandomState(G)
+    Q = 24
+    d = (rng.rand(Q, G) * 50 + 100).astype(np.float32)
+    gp = rng.randint(1000, 2000, G)                    # nobody's identity ...
+    gc = rng.randint(0, 3, G)
+    qp, qc = np.arange(Q), np.zeros(Q, int)
+    for q in range(Q):
+        cols = rng.choice(G, 3, replace=False)
+        kind = q % 6
+        if kind == 0:                                   # exactly one relevant item
+            gp[cols[0]] = q; gc[cols[0]] = 1
+        elif kind == 1:                                 # two relevant items, equal distance (span 0, R = 2)
+            gp[cols[:2]] = q; gc[cols[:2]] = 1
+            d[q, cols[1]] = d[q, cols[0]]
+        elif kind == 2:                                 # two relevant items one ulp apart
+            gp[cols[:2]] = q; gc[cols[:2]] = 1
+            d[q, cols[1]] = np.nextafter(d[q, cols[0]], np.float32(1e9))
+        elif kind == 3:                                 # enormous span: one relevant item at 1e30
+            gp[cols[:2]] = q; gc[cols[:2]] = 1
+            d[q, cols[1]] = 1e30
+        elif kind == 4:                                 # one relevant item tied with many others
+            gp[cols[0]] = q; gc[cols[0]] = 1
+            d[q, ::5] = d[q, cols[0]]
+        else:                                           # one relevant + one junk item
+            gp[cols[:2]] = q; gc[cols[0]] = 1; gc[cols[1]] = 0
+    check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
+
+
 def test_unaligned_rows_and_device_input():
     s = make_retrieval_set(33, 1001, 12, 3, dim=64, sigma=2.0, seed=6)     # G odd: rows start at any 4-byte offset
     d = R.compute_distance_matrix(s.qf, s.gf).numpy()
