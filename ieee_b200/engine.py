@@ -77,6 +77,16 @@ def _stages_for(Qb, cap, world, device, width=0):
 
 
 _FUSED_POOL = {}
+_RESULT_HOST = {}
+
+
+def _result_buffer(device, nbytes):
+    """Pinned host landing zone for the (cmc, summary, stats) read-back of one evaluation."""
+    key = (str(device), nbytes)
+    buf = _RESULT_HOST.get(key)
+    if buf is None:
+        buf = _RESULT_HOST[key] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    return buf
 
 
 def _fused_buffers(Q, D, precision, cap, k_eff, device):
@@ -156,8 +166,12 @@ class RetrievalEvaluator:
             # the gallery as packed row chunks [(first row, PackedFeatures)]: one chunk when the features are already
             # in HBM, several when they are streamed from the host (from_host) so that the contraction of chunk i
             # overlaps the PCIe copy of chunk i + 1
-            self.labels = GalleryLabels(g_pids, g_camids, self.device, overlap=True)     # side stream, beside the packing
+            # the big kernel first: the host work below (label copies, grouping on the side stream) then runs while
+            # the GPU packs, instead of in front of an idle GPU
             self.chunks = [(0, PackedFeatures(gf, dist_metric, normalize_feature, self.precision))] if gf is not None else []
+            # grouping: three tiny kernels behind the pack on the same stream (a side stream costs more host time than
+            # they take; the capacity query, when one is needed, still runs beside the contraction: list_cap_async)
+            self.labels = GalleryLabels(g_pids, g_camids, self.device)
         self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
@@ -174,7 +188,7 @@ class RetrievalEvaluator:
         Qb = dist.shape[0]
         st = _stages_for(Qb, cap, self.world, self.device, width)
         torch.cuda.current_stream().wait_event(self.labels.ready)
-        st.gather(dist, qp, qc, self.labels, self.g_offset)
+        st.gather(dist, qp, qc, self.labels, self.g_offset, stats=ties)     # kernels max / add straight into `ties`
         TRACE.mark("  gather")
         if self.world > 1:
             import torch.distributed as dist_
@@ -188,9 +202,6 @@ class RetrievalEvaluator:
             TRACE.mark("  all-reduce of counts")
         else:
             st.count(dist, self.G, self.g_offset)
-        ties[0:1] += st.flags[1:2]
-        ties[1:2] += st.flags[0:1] & 0xFFFFFFFF      # gather's overflow word (needed capacity, 0 = all lists fitted)
-        torch.maximum(ties[2:3], st.flags[2:3], out=ties[2:3])      # longest merged list (sizes the next call's rows)
         _lib.call("ieee_rank_query_metrics", st.counts.data_ptr(), Qb, self.g_total, 1, st.width, self.max_rank,
                   ap.data_ptr(), first.data_ptr(), short.data_ptr(), inp.data_ptr(), _lib.stream())
         TRACE.mark("  query metrics")
@@ -287,6 +298,10 @@ class RetrievalEvaluator:
         with torch.cuda.device(self.device):
             TRACE.mark("evaluate: start")
             Q = qf.shape[0]
+            rows = self._block_rows(Q)
+            # queries already in HBM: pack the first block before anything else, so the GPU is busy while the host
+            # prepares the rest of the step
+            early_pack = PackedFeatures(qf[: min(Q, rows)], self.metric, self.normalize, self.precision) if qf.is_cuda else None
             # small label copies go FIRST: host->device transfers of every stream share one copy engine queue, so a
             # label copy issued after the feature copies would hold the compute stream until they have all landed
             qp = _as_device(q_pids, torch.int64, self.device)
@@ -328,8 +343,8 @@ class RetrievalEvaluator:
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
             inp = torch.empty(Q, dtype=torch.float64, device=self.device)
-            ties = torch.zeros(3, dtype=torch.int64, device=self.device)        # [tie pairs, list overflow, longest merged list]
-            rows = self._block_rows(Q)
+            # [gather overflow = needed capacity (int32, 0: all lists fitted), tie pairs, longest merged list, pad]
+            ties = torch.zeros(4, dtype=torch.int64, device=self.device)
             if self._block is None or self._block.shape[0] < rows:
                 # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
                 # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
@@ -350,6 +365,8 @@ class RetrievalEvaluator:
                 return out
 
             def qf_packed(s, e):
+                if s == 0 and early_pack is not None:
+                    return early_pack
                 if q_event is not None:
                     torch.cuda.current_stream().wait_event(q_event)
                 return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
@@ -392,13 +409,18 @@ class RetrievalEvaluator:
             cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
             summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
             TRACE.mark("rank stages done")
-            _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr(),
+            _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr() + 8,
                       cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
-            out = torch.cat([cmc.view(torch.uint8), summ, ties[1:3].view(torch.uint8)]).cpu().numpy()   # one D2H copy, synchronises
+            host = _result_buffer(self.device, 4 * k_eff + 64 + 32)            # pinned: three small async copies, one sync
+            host[: 4 * k_eff].copy_(cmc.view(torch.uint8), non_blocking=True)
+            host[4 * k_eff: 4 * k_eff + 64].copy_(summ, non_blocking=True)
+            host[4 * k_eff + 64: 4 * k_eff + 96].copy_(ties.view(torch.uint8), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out = host.numpy()
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
             summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff: 4 * k_eff + 64].tobytes())
-            overflow, longest = (int(v) for v in out[4 * k_eff + 64:].view(np.int64)[:2])
+            overflow, _, longest = (int(v) for v in out[4 * k_eff + 64: 4 * k_eff + 96].view(np.int64)[:3])
             overflow = overflow or (longest > (width if width > 0 else self.world * cap))   # rows narrower than a merged list
             if memo_key is not None and not overflow:
                 if len(_CAP_MEMO) > 64:

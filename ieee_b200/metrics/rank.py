@@ -55,12 +55,15 @@ class GalleryLabels:
         self._scratch = torch.empty(64, dtype=torch.int32, device=device)
         with torch.cuda.device(device):
             cur = torch.cuda.current_stream()
-            stream = side_stream(device) if overlap else cur
             if overlap:
+                stream = side_stream(device)
                 stream.wait_stream(cur)                    # label copies / allocations queued so far
-            with torch.cuda.stream(stream):
-                _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
-                self.ready = stream.record_event()         # grouping queued up to here
+                with torch.cuda.stream(stream):
+                    _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), _lib.stream())
+                    self.ready = stream.record_event()     # grouping queued up to here
+            else:
+                _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), cur.cuda_stream)
+                self.ready = cur.record_event()
 
     def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
         """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
@@ -104,25 +107,31 @@ class RankStages:
         self.counts = torch.empty((Q, self.width + 2), dtype=torch.int32, device=device)
         # [0] gather overflow (int32), [1] tie pairs (uint64), [2] longest merged list (uint64)
         self.flags = torch.zeros(8, dtype=torch.int64, device=device)
+        self._stats = self.flags
         self.cmc = None
         self.summary = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=device)
         self.ap = torch.empty(Q, dtype=torch.float64, device=device)
         self.first = torch.empty(Q, dtype=torch.int32, device=device)
         self.ws = torch.empty(_lib.load().ieee_rank_finalize_workspace_bytes(Q), dtype=torch.uint8, device=device)
 
-    def gather(self, distmat, q_pids, q_camids, gal: GalleryLabels, g_offset: int = 0):
-        self.flags.zero_()
+    def gather(self, distmat, q_pids, q_camids, gal: GalleryLabels, g_offset: int = 0, stats=None):
+        """stats: an int64[>= 3] device tensor laid out like `flags` that the kernels max / add into (the caller zeroes
+        it once and lets several query blocks accumulate); default: this object's own `flags`, zeroed here."""
+        if stats is None:
+            self.flags.zero_()
+            stats = self.flags
+        self._stats = stats
         _lib.call("ieee_rank_gather", distmat.data_ptr(), distmat.stride(0), self.Q, gal.G, q_pids.data_ptr(),
                   q_camids.data_ptr(), gal.camids.data_ptr(), gal.group.data_ptr(), g_offset, self.cap,
                   self.rel.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
-                  self.flags.data_ptr(), _lib.stream())
+                  stats.data_ptr(), _lib.stream())
 
     def count(self, distmat, G: int, g_offset: int = 0, rel_all=None):
         """rel_all: the all-gathered relevant lists [shards, Q, cap + 1] (this rank's own list on one GPU)."""
         rel_all = self.rel if rel_all is None else rel_all
         _lib.call("ieee_rank_count", distmat.data_ptr(), distmat.stride(0), self.Q, G, g_offset, self.shards, self.cap,
                   self.width, rel_all.data_ptr(), self.n_rel.data_ptr(), self.junk.data_ptr(), self.n_junk.data_ptr(),
-                  self.counts.data_ptr(), self.flags.data_ptr() + 8, _lib.stream())
+                  self.counts.data_ptr(), self._stats.data_ptr() + 8, _lib.stream())
 
     def finalize(self, G_total: int, max_rank: int, counts=None, ties=None):
         """counts: the all-reduced count table (this rank's own on one GPU)."""

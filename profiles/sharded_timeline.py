@@ -22,12 +22,20 @@ s = market1501_shaped(num_q=3368 * world)
 g0, g1 = shard_bounds(s.gf.shape[0], world, rank)
 qf, gf = s.qf.to(dev), s.gf[g0:g1].to(dev)
 lab = [torch.from_numpy(x).to(dev) for x in (s.q_pids, s.q_camids, s.g_pids[g0:g1].copy(), s.g_camids[g0:g1].copy())]
-for it in range(6):
-    engine.TRACE.enabled = rank == 0 and it == 5
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev = RetrievalEvaluator(gf, lab[2], lab[3], group=dist.group.WORLD, g_offset=g0, g_total=s.gf.shape[0])
+report = engine.TRACE.report
+engine.TRACE.report = lambda: None                 # keep the marks of two consecutive steps on one time axis
+group = dist.group.WORLD if world > 1 else None
+for it in range(7):
+    engine.TRACE.enabled = rank == 0 and it >= 5
+    if it <= 5:
+        dist.barrier()
+        torch.cuda.synchronize()
+    engine.TRACE.mark("STEP %d begins (evaluator constructed next)" % it)
+    ev = RetrievalEvaluator(gf, lab[2], lab[3], group=group, g_offset=g0, g_total=s.gf.shape[0])
+    engine.TRACE.mark("evaluator constructed")
     cmc, mAP, info = ev.evaluate(qf, lab[0], lab[1])
+    engine.TRACE.mark("result on the host")
+report()
 if rank == 0:
     print("world %d: mAP %.4f rank-1 %.4f cap %d memo %s" % (world, mAP, cmc[0], info["cap"], list(engine._CAP_MEMO.values())))
 dist.destroy_process_group()
