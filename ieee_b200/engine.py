@@ -343,8 +343,11 @@ class RetrievalEvaluator:
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
             inp = torch.empty(Q, dtype=torch.float64, device=self.device)
-            # [gather overflow = needed capacity (int32, 0: all lists fitted), tie pairs, longest merged list, pad]
-            ties = torch.zeros(4, dtype=torch.int64, device=self.device)
+            # one result block = one device->host copy: [stats int64[4] | summary (64 B) | cmc float32[K']];
+            # stats = [gather overflow = needed capacity (int32, 0: all lists fitted), tie pairs, longest merged list, pad]
+            k_eff = min(self.max_rank, self.g_total)
+            res = torch.zeros(32 + 64 + 4 * k_eff, dtype=torch.uint8, device=self.device)
+            ties = res[:32].view(torch.int64)
             if self._block is None or self._block.shape[0] < rows:
                 # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
                 # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
@@ -405,22 +408,18 @@ class RetrievalEvaluator:
             if self.world > 1:
                 import torch.distributed as dist_
                 dist_.all_reduce(ties[:2], group=self.group)      # [2] (longest merged list) is the same on every rank
-            k_eff = min(self.max_rank, self.g_total)
-            cmc = torch.empty(k_eff, dtype=torch.float32, device=self.device)
-            summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=self.device)
+            summ, cmc = res[32:96], res[96:].view(torch.float32)
             TRACE.mark("rank stages done")
             _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr() + 8,
                       cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
-            host = _result_buffer(self.device, 4 * k_eff + 64 + 32)            # pinned: three small async copies, one sync
-            host[: 4 * k_eff].copy_(cmc.view(torch.uint8), non_blocking=True)
-            host[4 * k_eff: 4 * k_eff + 64].copy_(summ, non_blocking=True)
-            host[4 * k_eff + 64: 4 * k_eff + 96].copy_(ties.view(torch.uint8), non_blocking=True)
+            host = _result_buffer(self.device, res.numel())                    # pinned landing zone
+            host.copy_(res, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             out = host.numpy()
-            cmc_host = out[: 4 * k_eff].view(np.float32).copy()
-            summary = _lib.EvalSummary.from_buffer_copy(out[4 * k_eff: 4 * k_eff + 64].tobytes())
-            overflow, _, longest = (int(v) for v in out[4 * k_eff + 64: 4 * k_eff + 96].view(np.int64)[:3])
+            overflow, _, longest = (int(v) for v in out[:32].view(np.int64)[:3])
+            summary = _lib.EvalSummary.from_buffer_copy(out[32:96].tobytes())
+            cmc_host = out[96:].view(np.float32).copy()
             overflow = overflow or (longest > (width if width > 0 else self.world * cap))   # rows narrower than a merged list
             if memo_key is not None and not overflow:
                 if len(_CAP_MEMO) > 64:
