@@ -227,7 +227,7 @@ def run_ours(args):
     e2e_value = Q * args.steps / (ms_e2e / 1e3)
     # whole job: every rank copies its gallery shard and 1/N of the queries (all-gathered over NVLink) plus the labels
     h2d = (Q + G_TOTAL) * DIM * 4 + world * (2 * Q * 8) + 2 * G_TOTAL * 8
-    d2h = 4 * MAX_RANK + 64 + 4      # cmc + summary block + the list-capacity int
+    d2h = 32 + 64 + 4 * MAX_RANK     # one result block per step: stats (32 B) + summary (64 B) + cmc
 
     # ---- per-kernel timing for the roofline (live, CUDA events on the launching stream) -------------------
     Gs = g1 - g0
@@ -319,7 +319,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "result": {"mAP": mAP, "rank1": float(cmc[0]), "num_valid": int(info["num_valid"]), "num_ties": int(info["num_ties"])},
+            "result": {"mAP": mAP, "rank1": float(cmc[0]), "mINP": info.get("mINP"), "num_valid": int(info["num_valid"]),
+                       "num_ties": int(info["num_ties"])},
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

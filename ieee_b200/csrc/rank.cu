@@ -442,24 +442,26 @@ __device__ __forceinline__ void warp_visit8(WarpCount& c, const float4& u, const
   }
 }
 
-__device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane) {
+// `team` warps stream one row together: warp `wq` of the team takes every team-th group of 32 float4.
+__device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane, int wq, int team) {
   const float* __restrict__ row = c.row;
   const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
   int head = (int)(((16 - (addr & 15)) & 15) >> 2);
   if (head > G) head = G;
   const int nvec = (G - head) >> 2;
   const float4* rv = reinterpret_cast<const float4*>(row + head);
+  const int S = 32 * team, t0 = wq * 32 + lane;
   auto one = [&](int g) {
     const float d = row[g];
     const uint32_t ce = c.cell[warp_cell_index(d, c.lo, c.scale, c.top)];
     warp_bump(c, ce & 0xFF80u, 1);
     if (ce & 1u) warp_fix(c, d, (uint32_t)g);
   };
-  for (int g = lane; g < head; g += 32) one(g);
-  int i = lane;
-  for (; i + 96 < nvec; i += 128) {          // 4 independent 16-byte loads in flight per lane
+  for (int g = t0; g < head; g += S) one(g);
+  int i = t0;
+  for (; i + 3 * S < nvec; i += 4 * S) {     // 4 independent 16-byte loads in flight per lane
     // plain (L1-allocating) loads: the rare exact pass below re-reads a distance, and finds it in L1
-    const float4 a0 = __ldg(rv + i), a1 = __ldg(rv + i + 32), a2 = __ldg(rv + i + 64), a3 = __ldg(rv + i + 96);
+    const float4 a0 = __ldg(rv + i), a1 = __ldg(rv + i + S), a2 = __ldg(rv + i + 2 * S), a3 = __ldg(rv + i + 3 * S);
     uint32_t mask = 0;
     warp_visit8(c, a0, a1, mask);
     warp_visit8(c, a2, a3, mask);
@@ -468,159 +470,187 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane)
       const int bit = 31 - __clz(mask);
       mask &= ~(1u << bit);
       const int e = 15 - bit;
-      const int g = head + 4 * (i + (e >> 2) * 32) + (e & 3);
+      const int g = head + 4 * (i + (e >> 2) * S) + (e & 3);
       warp_fix(c, __ldg(row + g), (uint32_t)g);
     }
   }
-  for (; i < nvec; i += 32) {
+  for (; i < nvec; i += S) {
     const int g0 = head + 4 * i;
     one(g0); one(g0 + 1); one(g0 + 2); one(g0 + 3);
   }
-  for (int g = head + 4 * nvec + lane; g < G; g += 32) one(g);
+  for (int g = head + 4 * nvec + t0; g < G; g += S) one(g);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// count, warp-per-query variant: for short rows (G <= 64K) the per-CTA setup of rank_count_kernel (sort, cell
-// table, zeroing and folding 256 private columns, ~8000 warp instructions) costs more than streaming the row.
-// Here every warp owns one query and does its setup with warp-level primitives only (~500 instructions);
-// eight queries per CTA.  Needs R <= 64 thresholds and finite threshold distances, else the warp falls back to
-// the generic search with shared atomics on its own histogram.
+// count kernel.  WPQ = warps per query:
+//   WPQ = 1  eight queries per CTA, one warp each: short rows (G <= 64K), where a CTA-wide setup would cost more
+//            than streaming the row; all setup is done with warp-level primitives.
+//   WPQ = 8  one query per CTA: long rows (one C4 shard is 125 000 elements).  Warp 0 does the same setup, then
+//            all eight warps stream interleaved groups of the row into their own private counter columns.
+// Up to kWarpRmax thresholds per query; non-finite threshold distances or more than 64 thresholds in one cell
+// take the generic search with shared atomics.  Longer lists go to rank_count_kernel below.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWarpQ = 8;            // queries (warps) per CTA
+constexpr int kWarpQ = 8;            // warps per CTA
 constexpr int kWarpRmax = 128;       // thresholds per query the private table holds (cell words address up to 511 bins)
-// T[rmax] u64 | hist[rmax + 2] | cell[1024 + 2 (+2: keeps priv 8-byte aligned, it doubles as u64 staging)] u16 | priv[rmax + 2][32]
-__host__ __device__ inline int warp_smem_per_query(int rmax) {
-  return ((rmax * 8 + (rmax + 2) * 4 + (kLutCells + 4) * 2 + (rmax + 2) * 32 * 4) + 15) & ~15;
+struct WarpMisc { float lo, scale, top; int R, use_lut, ties; uint32_t kmax; int pad; };   // 32 bytes
+// T[rmax] u64 | hist[rmax + 2] | cell[1024 + 4] u16 | misc (32 B) | priv[wpq][rmax + 2][32]   (priv 8-byte aligned: it
+// doubles as the u64 staging area of the unsorted thresholds)
+__host__ __device__ inline int warp_smem_per_query(int rmax, int wpq) {
+  return ((rmax * 8 + (rmax + 2) * 4 + (kLutCells + 4) * 2 + 32 + wpq * (rmax + 2) * 32 * 4) + 15) & ~15;
 }
 
+template <int WPQ>
 __global__ void __launch_bounds__(32 * kWarpQ)
 rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
                        int out_cap, int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                        const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                        unsigned long long* __restrict__ ties_out) {
+  static_assert(WPQ == 1 || WPQ == kWarpQ, "one warp or the whole CTA per query");
+  constexpr bool kTeam = WPQ > 1;
   extern __shared__ __align__(16) uint8_t ws_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint8_t* mine = ws_raw + size_t(w) * warp_smem_per_query(rmax);
+  const int wq = kTeam ? w : 0;                                                       // this warp's place in its team
+  uint8_t* mine = ws_raw + (kTeam ? size_t(0) : size_t(w) * warp_smem_per_query(rmax, 1));
   uint64_t* T = reinterpret_cast<uint64_t*>(mine);                                   // [rmax]
   int32_t* hist = reinterpret_cast<int32_t*>(mine + rmax * 8);                        // [rmax + 2]
-  uint16_t* cell = reinterpret_cast<uint16_t*>(hist + rmax + 2);                      // [1024 + 2]
-  int32_t* priv = reinterpret_cast<int32_t*>(cell + kLutCells + 4);                   // [rmax + 2][32]
-  const int64_t q = (int64_t)blockIdx.x * kWarpQ + w;
+  uint16_t* cell = reinterpret_cast<uint16_t*>(hist + rmax + 2);                      // [1024 + 4]
+  WarpMisc* misc = reinterpret_cast<WarpMisc*>(cell + kLutCells + 4);
+  int32_t* priv = reinterpret_cast<int32_t*>(misc + 1) + size_t(wq) * (rmax + 2) * 32;   // this warp's [rmax + 2][32]
+  auto team_sync = [&]() { if constexpr (kTeam) __syncthreads(); else __syncwarp(); };
+  const int64_t q = kTeam ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * kWarpQ + w;
   if (q >= Q) return;
   const int stride = out_cap + 2;
   int32_t* out = counts + q * stride;
   const int nj = n_junk[q];
   int Rtot = 0;
   for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
-  if (lane == 0) {
+  if (lane == 0 && wq == 0) {
     out[stride - 1] = nj; out[stride - 2] = n_rel[q];
     // longest merged list seen: sizes the next call's rows (out_cap); a list longer than this call's is flagged by it
     if (ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
   }
   if (Rtot == 0 || Rtot > rmax) return;     // invalid query (rank.py:142-144) / row too small: caller re-runs
-  // thresholds of all shards, staged in `priv` (not live yet)
-  uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
-  int R = 0;
-  for (int s = 0; s < shards; ++s) {
-    const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
-    const int n = (int)src[cap];
-    for (int i = lane; i < n; i += 32) Tin[R + i] = src[i];
-    R += n;
-  }
-  __syncwarp();
-  // rank sort (keys are distinct)
-  for (int k = lane; k < R; k += 32) {
-    const uint64_t me = Tin[k];
-    int pos = 0;
-    for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
-    T[pos] = me;
-  }
-  __syncwarp();
-  for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;     // own column only: i % 32 == lane
-  const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
-  const float lo = key_to_float(kmin), hi = key_to_float(kmax);
-  const float span = hi - lo;
+  const int R = Rtot;
   const int L = lut_cells_for(G);
-  bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi);
-  // (hi - lo) * scale = L - 0.5: every threshold lands in cells 1 .. L and the map stays monotone (the -0.5 margin
-  // dwarfs fp32 rounding); everything else falls into the guard cells 0 and L + 1.  Any finite positive scale is
-  // CORRECT (cells only pre-sort, occupied cells compare exactly), so a single threshold or a tiny span (scale
-  // would overflow) just clamps it: d == lo -> cell 1, anything above -> beyond the table.
-  const float scale = use_lut ? fminf(((float)L - 0.5f) / span, 1.2676506e30f /* 2^100 */) : 0.f;
-  const float top = (float)(L + 1);
-  if (use_lut) {
-    // cell of every (sorted) threshold: non-decreasing in k; kept in `hist` (not live yet) as the search array
-    uint16_t* tcell = reinterpret_cast<uint16_t*>(hist);
-    for (int k = lane; k < R; k += 32) {
-      const uint32_t ci = warp_cell_index(key_to_float((uint32_t)(T[k] >> 32)), lo, scale, top);
-      tcell[k] = (uint16_t)min(max(ci, 1u), (uint32_t)L);
+  if (wq == 0) {                             // ---- setup by the team's first warp --------------------------------
+    // thresholds of all shards, staged in this warp's `priv` (not live yet)
+    uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
+    int base = 0;
+    for (int s = 0; s < shards; ++s) {
+      const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
+      const int n = (int)src[cap];
+      for (int i = lane; i < n; i += 32) Tin[base + i] = src[i];
+      base += n;
     }
     __syncwarp();
-    // Cell words in three warp-wide steps (O(L / 32) per lane, no per-cell search):
-    //   1. clear the table; 2. the first threshold of every run of equal cells writes that cell's word
-    //   (first bin = its rank k, count = run length; bit 0 marks the cell as occupied); 3. every empty cell
-    //   inherits "first bin" = a + n of the nearest occupied cell below it: each lane owns a contiguous chunk of
-    //   cells, finds the last occupied one, the warp passes those values upwards, and a second walk fills in.
-    uint32_t* cell32 = reinterpret_cast<uint32_t*>(cell);
-    for (int i = lane; i < (L + 4) / 2; i += 32) cell32[i] = 0;
-    __syncwarp();
-    bool crowded = false;                     // a cell word counts at most 64 thresholds
+    // rank sort (keys are distinct)
     for (int k = lane; k < R; k += 32) {
-      const int cidx = tcell[k];
-      if (k == 0 || (int)tcell[k - 1] != cidx) {
-        int n = 1;
-        while (k + n < R && (int)tcell[k + n] == cidx) ++n;
-        crowded |= n > 64;
-        cell[cidx] = warp_cell_word(k, min(n, 64));
+      const uint64_t me = Tin[k];
+      int pos = 0;
+      for (int j = 0; j < R; ++j) pos += (Tin[j] < me);
+      T[pos] = me;
+    }
+    __syncwarp();
+    const uint32_t kmin = (uint32_t)(T[0] >> 32), kmax = (uint32_t)(T[R - 1] >> 32);
+    const float lo = key_to_float(kmin), hi = key_to_float(kmax);
+    const float span = hi - lo;
+    bool use_lut = (kmax != 0xFFFFFFFFu) && isfinite(lo) && isfinite(hi);
+    // (hi - lo) * scale = L - 0.5: every threshold lands in cells 1 .. L and the map stays monotone (the -0.5 margin
+    // dwarfs fp32 rounding); everything else falls into the guard cells 0 and L + 1.  Any finite positive scale is
+    // CORRECT (cells only pre-sort, occupied cells compare exactly), so a single threshold or a tiny span (scale
+    // would overflow) just clamps it: d == lo -> cell 1, anything above -> beyond the table.
+    const float scale = use_lut ? fminf(((float)L - 0.5f) / span, 1.2676506e30f /* 2^100 */) : 0.f;
+    const float top = (float)(L + 1);
+    if (use_lut) {
+      // cell of every (sorted) threshold: non-decreasing in k; kept in `hist` (not live yet)
+      uint16_t* tcell = reinterpret_cast<uint16_t*>(hist);
+      for (int k = lane; k < R; k += 32) {
+        const uint32_t ci = warp_cell_index(key_to_float((uint32_t)(T[k] >> 32)), lo, scale, top);
+        tcell[k] = (uint16_t)min(max(ci, 1u), (uint32_t)L);
       }
+      __syncwarp();
+      // Cell words in three warp-wide steps (O(L / 32) per lane, no per-cell search):
+      //   1. clear the table; 2. the first threshold of every run of equal cells writes that cell's word
+      //   (first bin = its rank k, count = run length; bit 0 marks the cell as occupied); 3. every empty cell
+      //   inherits "first bin" = a + n of the nearest occupied cell below it: each lane owns a contiguous chunk of
+      //   cells, finds the last occupied one, the warp passes those values upwards, and a second walk fills in.
+      uint32_t* cell32 = reinterpret_cast<uint32_t*>(cell);
+      for (int i = lane; i < (L + 4) / 2; i += 32) cell32[i] = 0;
+      __syncwarp();
+      bool crowded = false;                     // a cell word counts at most 64 thresholds
+      for (int k = lane; k < R; k += 32) {
+        const int cidx = tcell[k];
+        if (k == 0 || (int)tcell[k - 1] != cidx) {
+          int n = 1;
+          while (k + n < R && (int)tcell[k + n] == cidx) ++n;
+          crowded |= n > 64;
+          cell[cidx] = warp_cell_word(k, min(n, 64));
+        }
+      }
+      __syncwarp();
+      const int chunk = (L + 2 + 31) / 32;
+      const int c0 = lane * chunk, c1 = min(c0 + chunk, L + 2);
+      int last = -1;                            // first bin that follows this lane's last occupied cell
+      for (int i = c0; i < c1; ++i) {
+        const uint32_t cw = cell[i];
+        if (cw & 1u) last = (int)(cw >> 7) + (int)((cw >> 1) & 63u) + 1;
+      }
+      const uint32_t have = __ballot_sync(0xffffffffu, last >= 0) & ((1u << lane) - 1u);
+      const int src = have ? 31 - __clz(have) : lane;
+      const int below = __shfl_sync(0xffffffffu, last, src);
+      int run = have ? below : 0;
+      for (int i = c0; i < c1; ++i) {
+        const uint32_t cw = cell[i];
+        if (cw & 1u) run = (int)(cw >> 7) + (int)((cw >> 1) & 63u) + 1;
+        else cell[i] = (i == L + 1) ? warp_cell_word(R + 1, 0) : warp_cell_word(run, 0);
+      }
+      if (__any_sync(0xffffffffu, crowded)) use_lut = false;     // (generic search path below)
+      __syncwarp();
     }
-    __syncwarp();
-    const int chunk = (L + 2 + 31) / 32;
-    const int c0 = lane * chunk, c1 = min(c0 + chunk, L + 2);
-    int last = -1;                            // first bin that follows this lane's last occupied cell
-    for (int i = c0; i < c1; ++i) {
-      const uint32_t w = cell[i];
-      if (w & 1u) last = (int)(w >> 7) + (int)((w >> 1) & 63u) + 1;
+    for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
+    if (lane == 0) {
+      misc->lo = lo; misc->scale = scale; misc->top = top; misc->R = R; misc->use_lut = use_lut ? 1 : 0;
+      misc->ties = 0; misc->kmax = kmax;
     }
-    const uint32_t have = __ballot_sync(0xffffffffu, last >= 0) & ((1u << lane) - 1u);
-    const int src = have ? 31 - __clz(have) : lane;
-    const int below = __shfl_sync(0xffffffffu, last, src);
-    int run = have ? below : 0;
-    for (int i = c0; i < c1; ++i) {
-      const uint32_t w = cell[i];
-      if (w & 1u) run = (int)(w >> 7) + (int)((w >> 1) & 63u) + 1;
-      else cell[i] = (i == L + 1) ? warp_cell_word(R + 1, 0) : warp_cell_word(run, 0);
-    }
-    if (__any_sync(0xffffffffu, crowded)) use_lut = false;     // (generic search path below)
     __syncwarp();
   }
-  for (int i = lane; i < R + 2; i += 32) hist[i] = 0;
-  __syncwarp();
+  // every warp clears its own counter columns (warp 0: after the staging above); own column only: i % 32 == lane
+  for (int i = lane; i < (R + 2) * 32; i += 32) priv[i] = 0;
+  team_sync();
+  const float lo = misc->lo, scale = misc->scale, top = misc->top;
+  const bool use_lut = misc->use_lut != 0;
+  const uint32_t kmax = misc->kmax;
   const float* row = distmat + q * ld;
   int tie_local = 0;
   if (use_lut) {
     WarpCount c;
     c.T = T; c.cell = cell; c.col = reinterpret_cast<uint8_t*>(priv + lane); c.row = row;
     c.lo = lo; c.scale = scale; c.top = top; c.g_offset = (uint32_t)g_offset; c.ties = 0;
-    warp_count_stream(c, G, lane);
+    warp_count_stream(c, G, lane, wq, WPQ);
     tie_local = c.ties;
   } else {
     CountCtx c;
     c.T = T; c.cell = nullptr; c.hist = hist; c.priv = priv + lane;
-    c.lo = lo; c.hi = hi; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
+    c.lo = lo; c.hi = 0.f; c.scale = scale; c.kmax = kmax; c.R = R; c.trash = R + 1; c.L = L;
     c.g_offset = (uint32_t)g_offset; c.ties = 0;
-    count_stream<COUNT_SEARCH_ATOMIC, 32>(c, row, G, lane);
+    count_stream<COUNT_SEARCH_ATOMIC, 32 * WPQ>(c, row, G, wq * 32 + lane);
     tie_local = c.ties;
   }
   __syncwarp();
-  if (use_lut) {   // fold: lane l sums bins l and l + 32 over the 32 private columns (rotated reads: conflict-free)
+  if (use_lut) {   // fold: lane l sums bins l, l + 32, .. over the warp's 32 private columns (rotated reads: conflict-free)
     for (int b = lane; b <= R; b += 32) {
       int sum = 0;
       for (int j = 0; j < 32; ++j) sum += priv[b * 32 + ((j + lane) & 31)];
-      hist[b] = sum;
+      if constexpr (kTeam) atomicAdd(&hist[b], sum); else hist[b] = sum;
     }
-    __syncwarp();
   }
+  if constexpr (kTeam) {
+    for (int o = 16; o > 0; o >>= 1) tie_local += __shfl_xor_sync(0xffffffffu, tie_local, o);
+    if (lane == 0 && tie_local != 0) atomicAdd(&misc->ties, tie_local);
+    tie_local = 0;
+  }
+  team_sync();
+  if (wq != 0) return;
   for (int i = lane; i < nj; i += 32) {      // junk items were streamed too: take them out (rank.py:136-140)
     const uint64_t pe = junk[q * cap + i];
     const uint32_t ke = (uint32_t)(pe >> 32);
@@ -632,6 +662,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     atomicSub(&hist[a], 1);
   }
   for (int o = 16; o > 0; o >>= 1) tie_local += __shfl_xor_sync(0xffffffffu, tie_local, o);
+  if constexpr (kTeam) tie_local += misc->ties;
   __syncwarp();
   // counts[k] = sum_{b <= k} hist[b] - [T_k is a local row entry]
   int carry = 0;
@@ -842,16 +873,19 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
                "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
   if (out_cap == 0 || out_cap > shards * cap) out_cap = shards * cap;       // a merged list cannot be longer than this
-  if (G <= count_warp_max_g() && out_cap <= kWarpRmax && !(g_debug_flags & 16)) {     // short rows: one warp per query
+  if (out_cap <= kWarpRmax && !(g_debug_flags & 16)) {
     const int rmax = (out_cap + 1) & ~1;           // even: keeps the 8-byte alignment of every query's T
-    const size_t wsmem = size_t(kWarpQ) * warp_smem_per_query(rmax);
-    static size_t wattr = 0;
-    if (wsmem > 48 * 1024 && wsmem > wattr) {
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      wattr = wsmem;
+    const bool team = G > count_warp_max_g();      // long rows: the whole CTA streams one query
+    const size_t wsmem = team ? size_t(warp_smem_per_query(rmax, kWarpQ)) : size_t(kWarpQ) * warp_smem_per_query(rmax, 1);
+    auto kern = team ? rank_count_warp_kernel<kWarpQ> : rank_count_warp_kernel<1>;
+    static size_t wattr[2] = {0, 0};
+    if (wsmem > 48 * 1024 && wsmem > wattr[team]) {
+      IEEE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      wattr[team] = wsmem;
     }
-    rank_count_warp_kernel<<<(unsigned)((Q + kWarpQ - 1) / kWarpQ), 32 * kWarpQ, wsmem, stream>>>(
-        distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel, junk, n_junk, counts, ties);
+    const unsigned grid = team ? (unsigned)Q : (unsigned)((Q + kWarpQ - 1) / kWarpQ);
+    kern<<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel,
+                                               junk, n_junk, counts, ties);
     count_launch();
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
