@@ -134,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"market1501_shaped Q={Q_BASE} G={G_TOTAL} D={DIM} euclidean max_rank={MAX_RANK}"},
+        "config": {"workload": f"market1501_shaped Q={Q_BASE * max(1, args.gpus)} G={G_TOTAL} D={DIM} euclidean max_rank={MAX_RANK}"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind,
                          "sample": f"each step: first {sample_q} queries x full {G_TOTAL}-row gallery; torch CPU distance "
                                    f"({cores} threads) + rank_cy.evaluate_cy (single-threaded by construction)"},
@@ -292,7 +292,7 @@ def run_ours(args):
                                           "for f32 inputs, exact for bf16 inputs)", "bound": "tensor", "achieved": gemm1_tflops,
                                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm1_tflops / peaks["bf16_tflops"],
                                 "traffic": traffic_1p},
-        "roofline_rank_count": {"kernel": "rank_count_warp_kernel", "bound": "hbm", "achieved": count_gbs, "peak": peaks["hbm_gbs"],
+        "roofline_rank_count": {"kernel": "rank_count_warp_kernel<1> (one warp per query; rows of 15913 columns)", "bound": "hbm", "achieved": count_gbs, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": count_gbs / peaks["hbm_gbs"], "algorithmic_bytes": 4 * Q * Gs,
                                 "traffic": traffic_cnt},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},

@@ -123,6 +123,19 @@ def test_degenerate_threshold_spans(G):
     check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
 
 
+@pytest.mark.parametrize("G", [3000, 70001])
+def test_long_relevant_lists(G):
+    """Hundreds of relevant items per query (more than the 128 the private-counter kernels hold): the CTA-per-query
+    kernel with shared atomics, incl. ties and rows longer than 64K."""
+    rng = np.random.RandomState(G)
+    Q = 20
+    d = rng.rand(Q, G).astype(np.float32)
+    d[:, ::9] = np.round(d[:, ::9] * 8) / 8                      # ties between relevant and other items
+    gp, gc = rng.randint(0, 6, G), rng.randint(0, 3, G)
+    qp, qc = rng.randint(0, 6, Q), rng.randint(0, 3, Q)
+    check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
+
+
 def test_unaligned_rows_and_device_input():
     s = make_retrieval_set(33, 1001, 12, 3, dim=64, sigma=2.0, seed=6)     # G odd: rows start at any 4-byte offset
     d = R.compute_distance_matrix(s.qf, s.gf).numpy()
