@@ -131,9 +131,13 @@ def test_long_relevant_lists(G):
     Q = 20
     d = rng.rand(Q, G).astype(np.float32)
     d[:, ::9] = np.round(d[:, ::9] * 8) / 8                      # ties between relevant and other items
-    gp, gc = rng.randint(0, 6, G), rng.randint(0, 3, G)
-    qp, qc = rng.randint(0, 6, Q), rng.randint(0, 3, Q)
+    n_pid = 6 if G < 10000 else 14               # ~500 / ~5000 gallery items per identity (the kernel holds 8192)
+    gp, gc = rng.randint(0, n_pid, G), rng.randint(0, 3, G)
+    qp, qc = rng.randint(0, n_pid, Q), rng.randint(0, 3, Q)
     check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
+    if G > 10000:                                # beyond the shared-memory budget: a clear error, never a wrong answer
+        with pytest.raises(_lib.IeeeB200Error, match="shared-memory budget"):
+            evaluate_rank(d, qp % 4, gp % 4, qc, gc, max_rank=20)
 
 
 def test_unaligned_rows_and_device_input():
