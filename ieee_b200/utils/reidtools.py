@@ -3,12 +3,12 @@
 The reference argsorts the whole Q x G matrix on the host (reidtools.py:49) and then, per query, walks the sorted
 row skipping same-pid/same-camera entries until it has ``topk`` images (:109-145).  Only those first ``topk`` kept
 entries are ever used, so here they come from the junk-masked top-k kernel (``ieee_topk``: one streaming pass per
-row on the GPU, ties by gallery index) and the host only does what is host work: reading, resizing and pasting
-images with OpenCV exactly as the reference does (same constants, same border/resize order), or copying tracklet
-files for ``data_type='video'``.
+row on the GPU, ties by gallery index); the host does what is host work -- OpenCV reads / resizes / pastes for
+``data_type='image'``, file copies for ``'video'`` -- and produces the files the reference produces (same names,
+same pixels: tests/test_visrank.py against tests/golden/visrank_small.npz, written by the reference itself).
 
-Same name, arguments, prints and output files as the reference.  ``distmat`` is ranked in float32 (the engine hands
-over a float32 matrix, engine.py:399-400).
+Same name, arguments and prints as the reference.  ``distmat`` is ranked in float32 (the engine hands over a float32
+matrix, engine.py:399-400).
 """
 from __future__ import absolute_import, print_function
 
@@ -22,105 +22,94 @@ from ..metrics.rank import topk_ranked_list
 
 __all__ = ["visualize_ranked_results", "ranked_lists"]
 
-GRID_SPACING = 10           # reidtools.py:11-15
-QUERY_EXTRA_SPACING = 90
-BW = 5                      # border width
-GREEN = (0, 255, 0)
-RED = (0, 0, 255)
-
-
-def _mkdir_if_missing(dirname):
-    if dirname and not osp.exists(dirname):
-        os.makedirs(dirname, exist_ok=True)
-
-
-def _first_path(p):
-    return p[0] if isinstance(p, (tuple, list)) else p
+# layout constants of the reference's figure (reidtools.py:11-15)
+GRID_SPACING, QUERY_EXTRA_SPACING, BW = 10, 90, 5
+BLACK, GREEN, RED = (0, 0, 0), (0, 255, 0), (0, 0, 255)      # BGR: query frame, true match, false match
 
 
 def ranked_lists(distmat, dataset, topk=10):
-    """(idx int32 [Q, topk], matched bool [Q, topk]) -- the gallery entries reidtools.py:109-145 would show for
-    every query, in order; idx is -1 where a query keeps fewer than ``topk`` gallery items."""
+    """(idx int32 [Q, topk'], matched bool [Q, topk']) -- the gallery entries reidtools.py:109-145 would show for every
+    query, in order (topk' = min(topk, G)); idx is -1 where a query keeps fewer gallery items than that."""
     query, gallery = dataset
-    q_pids = np.asarray([q[1] for q in query], dtype=np.int64)
-    q_cams = np.asarray([q[2] for q in query], dtype=np.int64)
-    g_pids = np.asarray([g[1] for g in gallery], dtype=np.int64)
-    g_cams = np.asarray([g[2] for g in gallery], dtype=np.int64)
+    q_pid, q_cam = (np.asarray([e[i] for e in query], dtype=np.int64) for i in (1, 2))
+    g_pid, g_cam = (np.asarray([e[i] for e in gallery], dtype=np.int64) for i in (1, 2))
     k = max(1, min(int(topk), len(gallery)))
-    idx, _ = topk_ranked_list(distmat, q_pids, g_pids, q_cams, g_cams, k=k)
-    idx = idx.cpu().numpy()
+    idx = topk_ranked_list(distmat, q_pid, g_pid, q_cam, g_cam, k=k)[0].cpu().numpy()
+    found = idx >= 0
     matched = np.zeros(idx.shape, dtype=bool)
-    ok = idx >= 0
-    matched[ok] = g_pids[idx[ok]] == np.broadcast_to(q_pids[:, None], idx.shape)[ok]
+    matched[found] = g_pid[idx[found]] == np.broadcast_to(q_pid[:, None], idx.shape)[found]
     return idx, matched
+
+
+def _first(path):
+    """Entries of the fork's datasets carry one path per modality (RGB, NIR, TIR); the figure shows the first."""
+    return path[0] if isinstance(path, (tuple, list)) else path
+
+
+class _Figure:
+    """One query's grid: the query tile, a gap, then `topk` framed gallery tiles (reidtools.py:85-101,118-134)."""
+
+    def __init__(self, cv2, width, height, topk):
+        self.cv2, self.w, self.h = cv2, width, height
+        self.canvas = np.full((height, (topk + 1) * width + topk * GRID_SPACING + QUERY_EXTRA_SPACING, 3), 255, np.uint8)
+
+    def tile(self, path, frame):
+        cv2 = self.cv2
+        img = cv2.resize(cv2.imread(_first(path)), (self.w, self.h))
+        img = cv2.copyMakeBorder(img, BW, BW, BW, BW, cv2.BORDER_CONSTANT, value=frame)
+        return cv2.resize(img, (self.w, self.h))      # second resize: the frame ends up equally wide on every tile
+
+    def put(self, slot, path, frame):
+        x0 = 0 if slot == 0 else slot * (self.w + GRID_SPACING) + QUERY_EXTRA_SPACING
+        self.canvas[:, x0:x0 + self.w, :] = self.tile(path, frame)
+
+    def save(self, path):
+        self.cv2.imwrite(path, self.canvas)
+
+
+def _export(src, folder, label):
+    """Video mode (reidtools.py:51-76): a tracklet (tuple of frames) becomes a sub-folder, a single image a file."""
+    if isinstance(src, (tuple, list)):
+        dst = osp.join(folder, label)
+        os.makedirs(dst, exist_ok=True)
+        for frame in src:
+            shutil.copy(frame, dst)
+    else:
+        shutil.copy(src, osp.join(folder, label.split('_TRUE')[0].split('_FALSE')[0] + '_name_' + osp.basename(src)))
 
 
 def visualize_ranked_results(distmat, dataset, data_type, width=128, height=256, save_dir='', topk=10):
     """Visualizes ranked results (image-reid: one grid figure per query; video-reid: one folder per query with the
     ranked tracklets).  Arguments as torchreid/utils/reidtools.py:18-39."""
-    import cv2
-
     num_q, num_g = distmat.shape
-    _mkdir_if_missing(save_dir)
-
+    if save_dir:
+        os.makedirs(save_dir, exist_ok=True)
     print('# query: {}\n# gallery {}'.format(num_q, num_g))
     print('Visualizing top-{} ranks ...'.format(topk))
-
     query, gallery = dataset
     assert num_q == len(query)
     assert num_g == len(gallery)
+    idx, matched = ranked_lists(distmat, dataset, topk)
+    as_image = data_type == 'image'
+    if as_image:
+        import cv2
 
-    idx, matched_all = ranked_lists(distmat, dataset, topk)
-
-    def _cp_img_to(src, dst, rank, prefix, matched=False):      # reidtools.py:51-76
-        if isinstance(src, (tuple, list)):
-            if prefix == 'gallery':
-                suffix = 'TRUE' if matched else 'FALSE'
-                dst = osp.join(dst, prefix + '_top' + str(rank).zfill(3)) + '_' + suffix
-            else:
-                dst = osp.join(dst, prefix + '_top' + str(rank).zfill(3))
-            _mkdir_if_missing(dst)
-            for img_path in src:
-                shutil.copy(img_path, dst)
+    for q, entry in enumerate(query):
+        stem = osp.basename(osp.splitext(_first(entry[0]))[0])
+        shown = [(rank, int(g), bool(m)) for rank, (g, m) in enumerate(zip(idx[q], matched[q]), start=1) if g >= 0][:topk]
+        if as_image:
+            fig = _Figure(cv2, width, height, topk)
+            fig.put(0, entry[0], BLACK)
+            for rank, g, hit in shown:
+                fig.put(rank, gallery[g][0], GREEN if hit else RED)
+            fig.save(osp.join(save_dir, stem + '.jpg'))
         else:
-            dst = osp.join(dst, prefix + '_top' + str(rank).zfill(3) + '_name_' + osp.basename(src))
-            shutil.copy(src, dst)
-
-    def _tile(path, color):                                       # reidtools.py:85-92,118-130
-        img = cv2.imread(_first_path(path))
-        img = cv2.resize(img, (width, height))
-        img = cv2.copyMakeBorder(img, BW, BW, BW, BW, cv2.BORDER_CONSTANT, value=color)
-        return cv2.resize(img, (width, height))   # resized twice: consistent border width across images
-
-    for q_idx in range(num_q):
-        qimg_path, qpid, qcamid = query[q_idx][:3]
-        qimg_path_name = _first_path(qimg_path)
-
-        if data_type == 'image':
-            grid_img = 255 * np.ones((height, (topk + 1) * width + topk * GRID_SPACING + QUERY_EXTRA_SPACING, 3),
-                                     dtype=np.uint8)
-            grid_img[:, :width, :] = _tile(qimg_path, (0, 0, 0))
-        else:
-            qdir = osp.join(save_dir, osp.basename(osp.splitext(qimg_path_name)[0]))
-            _mkdir_if_missing(qdir)
-            _cp_img_to(qimg_path, qdir, rank=0, prefix='query')
-
-        for rank_idx, (g_idx, matched) in enumerate(zip(idx[q_idx], matched_all[q_idx]), start=1):
-            if g_idx < 0 or rank_idx > topk:
-                break
-            gimg_path = gallery[g_idx][0]
-            if data_type == 'image':
-                start = rank_idx * width + rank_idx * GRID_SPACING + QUERY_EXTRA_SPACING
-                end = (rank_idx + 1) * width + rank_idx * GRID_SPACING + QUERY_EXTRA_SPACING
-                grid_img[:, start:end, :] = _tile(gimg_path, GREEN if matched else RED)
-            else:
-                _cp_img_to(gimg_path, qdir, rank=rank_idx, prefix='gallery', matched=bool(matched))
-
-        if data_type == 'image':
-            imname = osp.basename(osp.splitext(qimg_path_name)[0])
-            cv2.imwrite(osp.join(save_dir, imname + '.jpg'), grid_img)
-
-        if (q_idx + 1) % 100 == 0:
-            print('- done {}/{}'.format(q_idx + 1, num_q))
+            folder = osp.join(save_dir, stem)
+            os.makedirs(folder, exist_ok=True)
+            _export(entry[0], folder, 'query_top000')
+            for rank, g, hit in shown:
+                _export(gallery[g][0], folder, 'gallery_top' + str(rank).zfill(3) + ('_TRUE' if hit else '_FALSE'))
+        if (q + 1) % 100 == 0:
+            print('- done {}/{}'.format(q + 1, num_q))
 
     print('Done. Images have been saved to "{}" ...'.format(save_dir))
