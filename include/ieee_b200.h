@@ -74,7 +74,8 @@ int ieee_set_cta_group(int cta_group);
  * Returns the previous value. */
 int ieee_set_accum_chunk(int k_slices);
 /* Diagnostics for kernel tuning (results are WRONG when non-zero): bit 0 = tensor-core epilogue skips its global
- * stores, bit 1 = epilogue also skips the TMEM reads, bit 2 = no TMA store, bit 3 = chunk BF16 mode too.  Returns the previous value. */
+ * stores, bit 1 = epilogue also skips the TMEM reads, bit 2 = no TMA store, bit 3 = chunk BF16 mode too, bit 4 = count
+ * stage always uses the CTA-per-query kernel with shared atomics (results stay correct).  Returns the previous value. */
 int ieee_set_debug_flags(int flags);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
 int64_t ieee_launch_count(void);
