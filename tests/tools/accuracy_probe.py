@@ -1,6 +1,6 @@
 """Numerical accuracy of the distance kernels vs float64, next to the reference's own fp32 result.
 
-    python profiles/accuracy_probe.py
+    python tests/tools/accuracy_probe.py
 
 Prints, for each precision mode and for torch-CPU fp32 (what the reference computes, distance.py:59-64):
 relative error over the pairs that are not near-duplicates, the error in units of |q|^2+|g|^2 (the
@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from ieee_b200.metrics import compute_distance_matrix
 from ieee_b200.testing import make_retrieval_set, rgbnt201_shaped
 from oracle import restatement as R
