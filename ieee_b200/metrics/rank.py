@@ -185,6 +185,8 @@ def eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank):
     if num_g < max_rank:
         max_rank = num_g
         print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    if num_q == 0 or num_g == 0:      # no query can have a kept match: the reference ends in its assertion (rank.py:165)
+        raise AssertionError("Error: all query identities do not appear in gallery")
     cmc, summary, _ = evaluate_device(d, q_pids, g_pids, q_camids, g_camids, max_rank)
     raise_for_status(summary, max_rank)
     return cmc.cpu().numpy(), float(summary.mAP)

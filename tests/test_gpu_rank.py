@@ -161,6 +161,9 @@ def test_max_rank_clamp_and_errors(capsys):
     assert np.array_equal(cmc, R.evaluate_rank(d, qp, gp, qc, gc, max_rank=50)[0])
     with pytest.raises(AssertionError, match="all query identities do not appear in gallery"):   # rank.py:165
         evaluate_rank(d, qp + 100, gp, qc, gc)
+    for empty in (np.zeros((0, 12), np.float32), np.zeros((6, 0), np.float32)):                 # empty query / gallery set
+        with pytest.raises(AssertionError, match="all query identities do not appear in gallery"):
+            evaluate_rank(empty, qp[:empty.shape[0]], gp[:empty.shape[1]], qc[:empty.shape[0]], gc[:empty.shape[1]])
     with pytest.raises(TypeError):                                                              # rank.py:236-239
         evaluate_rank(d, qp, gp, qc, gc, use_metric_cuhk03=True)
     with pytest.raises(ValueError, match="fewer than max_rank"):     # all but 2 gallery items junk for query 0
