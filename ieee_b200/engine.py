@@ -440,6 +440,14 @@ class RetrievalEvaluator:
         return cmc_host, float(summary.mAP), info
 
 
+def result_lines(cmc, mAP, ranks=(1, 5, 10, 20)):
+    """The result block ``Engine._evaluate`` prints (engine.py:420-425), line by line -- the format
+    tools/parse_test_res.py:70-74 parses ('mAP: 61.05%', 'Rank-1  : 89.33%', ...)."""
+    lines = ["** Results **", "mAP: {:.2%}".format(mAP), "CMC curve"]
+    lines += ["Rank-{:<3}: {:.2%}".format(r, cmc[r - 1]) for r in ranks if r - 1 < len(cmc)]
+    return lines + ["\n"]
+
+
 def evaluate(qf, gf, q_pids, g_pids, q_camids, g_camids, dist_metric="euclidean", normalize_feature=False, rerank=False,
              ranks=(1, 5, 10, 20), max_rank=20, precision=None, verbose=True, dataset_name=""):
     """Tail of ``Engine._evaluate`` (engine.py:391-441) on one GPU.  Feature tensors may live on the host
@@ -475,11 +483,6 @@ def evaluate(qf, gf, q_pids, g_pids, q_camids, g_camids, dist_metric="euclidean"
         cmc, mAP = cmc_t.cpu().numpy(), float(summary.mAP)
     if verbose:
         print("Computing CMC and mAP for {}".format(dataset_name))
-        print("** Results **")
-        print("mAP: {:.2%}".format(mAP))
-        print("CMC curve")
-        for r in ranks:
-            if r - 1 < len(cmc):
-                print("Rank-{:<3}: {:.2%}".format(r, cmc[r - 1]))
-        print("\n")
+        for line in result_lines(cmc, mAP, ranks):
+            print(line)
     return cmc, mAP

@@ -70,3 +70,30 @@ def test_shim_package_resolves_torchreid_names():
     env["PYTHONPATH"] = os.pathsep.join([shim.PATH, root])
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_result_lines_parse_with_the_references_log_parser():
+    """tools/parse_test_res.py:70-74 greps these five patterns out of test.log; the device-resident engine prints
+    through ieee_b200.engine.result_lines, so its logs keep parsing."""
+    import re
+
+    import numpy as np
+    from ieee_b200.engine import result_lines
+    cmc = np.linspace(0.5, 0.99, 20).astype(np.float32)
+    lines = result_lines(cmc, 0.61049, ranks=[1, 5, 10, 20])
+    assert lines[:3] == ["** Results **", "mAP: 61.05%", "CMC curve"] and lines[-1] == "\n"
+    patterns = {"mAP": r'mAP: ([\.\deE+-]+)%', "r1": r'Rank-1  : ([\.\deE+-]+)%', "r5": r'Rank-5  : ([\.\deE+-]+)%',
+                "r10": r'Rank-10 : ([\.\deE+-]+)%', "r20": r'Rank-20 : ([\.\deE+-]+)%'}
+    found = {}
+    for line in lines:
+        for key, pat in patterns.items():
+            m = re.compile(pat).search(line.strip())
+            if m:
+                found[key] = float(m.group(1))
+    assert found == {"mAP": 61.05, "r1": 50.0, "r5": round(float(cmc[4]) * 100, 2), "r10": round(float(cmc[9]) * 100, 2),
+                     "r20": 99.0}
+    if os.path.isfile("/root/reference/tools/parse_test_res.py"):            # the patterns above are the reference's
+        src = open("/root/reference/tools/parse_test_res.py").read()
+        for pat in patterns.values():
+            assert "r'%s'" % pat in src
+    assert result_lines(cmc[:3], 0.5, ranks=[1, 5]) == ["** Results **", "mAP: 50.00%", "CMC curve", "Rank-1  : 50.00%", "\n"]
