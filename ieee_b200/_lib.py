@@ -31,10 +31,15 @@ SIGNATURES = {
     "ieee_set_cta_group": (C.c_int, [C.c_int]),
     "ieee_launch_count": (i64, []),
     "ieee_set_debug_flags": (C.c_int, [C.c_int]),
+    "ieee_set_raster_panel": (C.c_int, [C.c_int]),
+    "ieee_set_centering": (C.c_int, [C.c_int]),
+    "ieee_feature_center_workspace_bytes": (sz, [i64]),
+    "ieee_feature_center": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, i64, vp, vp, vp]),
     "ieee_set_accum_chunk": (C.c_int, [C.c_int]),
     "ieee_packed_bytes": (sz, [i64, i64, C.c_int]),
-    "ieee_pack_features": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "ieee_distmat_packed": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp]),
+    "ieee_pack_features": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "ieee_distmat_fixup_bytes": (sz, [i64]),
+    "ieee_distmat_packed": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp, vp]),
     "ieee_distmat_workspace_bytes": (sz, [i64, i64, i64, C.c_int]),
     "ieee_distmat": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, i64, vp, sz, vp]),
     "ieee_gallery_group_bytes": (sz, [i64]),
@@ -50,11 +55,13 @@ SIGNATURES = {
     "ieee_rank_finalize": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "ieee_eval_workspace_bytes": (sz, [i64, i64, i32]),
     "ieee_eval_market1501": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
+    "ieee_gallery_prepare_workspace_bytes": (sz, [i64]),
+    "ieee_gallery_prepare": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, i64, vp, vp, vp, vp, vp]),
     "ieee_retrieve_workspace_bytes": (sz, [i64, i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval": (C.c_int, [vp, i64, vp, i64, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32,
                                      C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "ieee_retrieve_prepared_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
-    "ieee_retrieve_eval_prepared": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, vp, vp, vp, i32, i32,
+    "ieee_retrieve_eval_prepared": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, i32, i32,
                                               C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "ieee_topk": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
     "ieee_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),

@@ -1,5 +1,6 @@
 // extern "C" surface of libieee_b200.so (see include/ieee_b200.h).
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -17,7 +18,9 @@ const char* get_error() { return g_error; }
 
 static std::atomic<long long> g_launches{0};
 int g_debug_flags = 0;
-int g_accum_chunk_kb = 4;
+int g_accum_chunk_kb = 6;
+int g_raster_panel = 0;
+static int g_centering = 1;
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
@@ -34,9 +37,13 @@ int sm_count() {
 
 // implemented in the other translation units
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
-                  void* packed, cudaStream_t stream);
+                  const float* center, void* packed, cudaStream_t stream);
+size_t feature_center_workspace_bytes(int64_t D);
+int feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
+                   float* center, void* workspace, cudaStream_t stream);
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
-                 float* out, int64_t ldo, cudaStream_t stream, int cta_group);
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws);
+size_t distmat_fixup_bytes(int64_t Q);
 int distmat_simt(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, float* out,
                  int64_t ldo, cudaStream_t stream);
 size_t gallery_group_bytes(int64_t G);
@@ -101,6 +108,24 @@ struct Arena {
   }
 };
 
+
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideLane g_side[64];
+static std::mutex g_side_mutex;
+static int side_lane(SideLane** out) {
+  int dev = 0;
+  IEEE_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return IEEE_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideLane& l = g_side[dev];
+  if (l.stream == nullptr) {
+    IEEE_CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    IEEE_CUDA_CHECK(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    IEEE_CUDA_CHECK(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+  }
+  *out = &l;
+  return IEEE_OK;
+}
 }  // namespace ieee
 
 using namespace ieee;
@@ -136,6 +161,18 @@ int ieee_set_debug_flags(int flags) {
   return prev;
 }
 
+int ieee_set_raster_panel(int m_tiles) {
+  const int prev = g_raster_panel;
+  if (m_tiles >= 0) g_raster_panel = m_tiles;
+  return prev;
+}
+
+int ieee_set_centering(int on) {
+  const int prev = g_centering;
+  if (on >= 0) g_centering = on ? 1 : 0;
+  return prev;
+}
+
 int ieee_set_cta_group(int cg) {
   const int prev = cta_group_default();
   if (cg == 1 || cg == 2) g_cta_group = cg;
@@ -149,14 +186,32 @@ size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision) {
 }
 
 int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,
-                       int precision, void* packed, ieee_stream_t stream) {
+                       int precision, const float* center, void* packed, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
-  return pack_features(x, dtype, ld, rows, D, metric, normalize, precision, packed, (cudaStream_t)stream);
+  return pack_features(x, dtype, ld, rows, D, metric, normalize, precision, center, packed, (cudaStream_t)stream);
 }
 
+size_t ieee_feature_center_workspace_bytes(int64_t D) { return D > 0 ? feature_center_workspace_bytes(D) : 0; }
+
+int ieee_feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
+                        float* center, void* workspace, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return feature_center(x, dtype, ld, rows, D, normalize, max_rows, center, workspace, (cudaStream_t)stream);
+}
+
+// whether the one-call entry points centre the operands themselves: euclidean only (cosine is not translation
+// invariant), and not the 1-pass BF16 mode (bf16 inputs multiply exactly as they are)
+static bool auto_center(int metric, int precision) {
+  return g_centering && metric == IEEE_METRIC_EUCLIDEAN && precision != IEEE_PREC_BF16;
+}
+static size_t center_bytes(int64_t D) { return align256(size_t(D) * 4) + feature_center_workspace_bytes(D); }
+
+size_t ieee_distmat_fixup_bytes(int64_t Q) { return Q > 0 ? distmat_fixup_bytes(Q) : 0; }
+
 int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
-                        int precision, float* out, int64_t ldo, ieee_stream_t stream) {
+                        int precision, float* out, int64_t ldo, void* fixup_workspace, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
   IEEE_REQUIRE(q_packed && g_packed && out, "distmat: null pointer");
@@ -167,11 +222,14 @@ int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, i
   if (Q == 0 || G == 0) return IEEE_OK;
   if (precision == IEEE_PREC_FP32_SIMT) return distmat_simt(q_packed, Q, g_packed, G, D, metric, out, ldo, (cudaStream_t)stream);
   IEEE_REQUIRE(precision == IEEE_PREC_F16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
-  return distmat_umma(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, (cudaStream_t)stream, cta_group_default());
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(fixup_workspace) & 7) == 0, "distmat: fix-up workspace must be 8-byte aligned");
+  return distmat_umma(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, (cudaStream_t)stream, cta_group_default(),
+                      fixup_workspace);
 }
 
 size_t ieee_distmat_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision) {
-  return ieee_packed_bytes(Q, D, precision) + ieee_packed_bytes(G, D, precision) + 512;
+  return align256(ieee_packed_bytes(Q, D, precision)) + align256(ieee_packed_bytes(G, D, precision)) + center_bytes(D) +
+         distmat_fixup_bytes(Q) + 512;
 }
 
 int ieee_distmat(const void* q, const void* g, int dtype, int64_t ldq, int64_t ldg, int64_t Q, int64_t G, int64_t D,
@@ -187,9 +245,18 @@ int ieee_distmat(const void* q, const void* g, int dtype, int64_t ldq, int64_t l
   uint8_t* w = static_cast<uint8_t*>(workspace);
   void* qp = w;
   void* gp = w + align256(ieee_packed_bytes(Q, D, precision));
-  if ((rc = ieee_pack_features(q, dtype, ldq, Q, D, metric, normalize, precision, qp, stream))) return rc;
-  if ((rc = ieee_pack_features(g, dtype, ldg, G, D, metric, normalize, precision, gp, stream))) return rc;
-  return ieee_distmat_packed(qp, Q, gp, G, D, metric, precision, out, ldo, stream);
+  float* center = nullptr;
+  uint8_t* cbase = static_cast<uint8_t*>(gp) + align256(ieee_packed_bytes(G, D, precision));
+  void* fix = cbase + center_bytes(D);
+  if (auto_center(metric, precision) && Q > 0 && G > 0) {
+    // centre of the first operand (a sample of its rows): both sides are packed relative to it
+    center = reinterpret_cast<float*>(cbase);
+    void* cws = cbase + align256(size_t(D) * 4);
+    if ((rc = feature_center(q, dtype, ldq, Q, D, normalize, 0, center, cws, (cudaStream_t)stream))) return rc;
+  }
+  if ((rc = ieee_pack_features(q, dtype, ldq, Q, D, metric, normalize, precision, center, qp, stream))) return rc;
+  if ((rc = ieee_pack_features(g, dtype, ldg, G, D, metric, normalize, precision, center, gp, stream))) return rc;
+  return ieee_distmat_packed(qp, Q, gp, G, D, metric, precision, out, ldo, fix, stream);
 }
 
 // ---- ranking -------------------------------------------------------------------------------------------
@@ -323,6 +390,38 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
   return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
 }
 
+// ---- gallery preparation in one call ----------------------------------------------------------------------
+// A side stream per device for work that only depends on the labels (the grouping's tiny kernels run beside the
+// bandwidth-bound feature packing instead of in front of it).
+
+size_t ieee_gallery_prepare_workspace_bytes(int64_t D) { return D > 0 ? feature_center_workspace_bytes(D) : 0; }
+
+int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int64_t D, int metric, int normalize, int precision,
+                         const int64_t* g_pids, const void* center_src, int64_t ld_src, int64_t rows_src, float* center,
+                         void* g_packed, void* group, void* workspace, ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(gf && g_packed && G > 0 && D > 0, "gallery_prepare: bad arguments (G=%lld D=%lld)", (long long)G, (long long)D);
+  IEEE_REQUIRE(center_src == nullptr || (center != nullptr && workspace != nullptr && rows_src > 0),
+               "gallery_prepare: a centre source needs the centre buffer and the workspace");
+  SideLane* lane = nullptr;
+  const bool grouping = g_pids != nullptr && group != nullptr;
+  if (grouping) {
+    if ((rc = side_lane(&lane))) return rc;
+    IEEE_CUDA_CHECK(cudaEventRecord(lane->fork, stream));
+    IEEE_CUDA_CHECK(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+    if ((rc = gallery_group(g_pids, G, group, lane->stream))) return rc;
+    IEEE_CUDA_CHECK(cudaEventRecord(lane->join, lane->stream));
+  }
+  if (center_src != nullptr &&
+      (rc = feature_center(center_src, dtype, ld_src, rows_src, D, normalize, 0, center, workspace, stream)))
+    return rc;
+  if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, center, g_packed, stream))) return rc;
+  if (grouping) IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
+  return IEEE_OK;
+}
+
 // ---- retrieval + evaluation in one call ----------------------------------------------------------------
 static size_t retrieve_rank_bytes(int64_t Q, int32_t cap) {
   size_t b = 256;                                  // cap scratch + overflow flag + ties
@@ -336,18 +435,19 @@ static size_t retrieve_rank_bytes(int64_t Q, int32_t cap) {
 size_t ieee_retrieve_prepared_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap) {
   if (Q <= 0 || D <= 0) return 0;
   if (cap <= 0) cap = 4096;
-  return align256(ieee_packed_bytes(Q, D, precision)) + retrieve_rank_bytes(Q, cap) + 256;
+  return align256(ieee_packed_bytes(Q, D, precision)) + retrieve_rank_bytes(Q, cap) + distmat_fixup_bytes(Q) + 256;
 }
 
 size_t ieee_retrieve_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision, int32_t cap) {
   if (Q <= 0 || G <= 0 || D <= 0) return 0;
   if (cap <= 0) cap = (int32_t)(G < 4096 ? G : 4096);
-  return align256(ieee_packed_bytes(G, D, precision)) + align256(gallery_group_bytes(G)) +
+  return align256(ieee_packed_bytes(G, D, precision)) + align256(gallery_group_bytes(G)) + center_bytes(D) +
          ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap);
 }
 
 int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
-                                int precision, const void* g_packed, const void* group, int64_t G, const int64_t* q_pids,
+                                int precision, const void* g_packed, const void* group, const float* center, int64_t G,
+                                const int64_t* q_pids,
                                 const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank, int32_t cap,
                                 int32_t* cap_host_out, float* distmat, int64_t ld, float* cmc, ieee_eval_summary* summary,
                                 double* per_query_ap, int32_t* per_query_first, void* workspace, size_t workspace_bytes,
@@ -363,8 +463,9 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
   void* q_packed = a.take(ieee_packed_bytes(Q, D, precision));
   int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
-  if (!q_packed || !scratch) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
-  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, q_packed, stream))) return rc;
+  void* fix = a.take(distmat_fixup_bytes(Q));
+  if (!q_packed || !scratch || !fix) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
   if (cap <= 0) {
     int32_t need = 0;
     if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
@@ -382,7 +483,7 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
               ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap), cap);
     return IEEE_ERR_WORKSPACE;
   }
-  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, stream_))) return rc;
+  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
   IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
@@ -406,12 +507,18 @@ int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg,
   Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
   void* g_packed = a.take(ieee_packed_bytes(G, D, precision));
   void* group = a.take(gallery_group_bytes(G));
-  if (!g_packed || !group) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
-  // labels first: the grouping is three tiny kernels, and a capacity query (cap <= 0) only waits for them
-  if ((rc = gallery_group(g_pids, G, group, stream))) return rc;
-  if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, g_packed, stream))) return rc;
+  float* center = static_cast<float*>(a.take(size_t(D) * 4));
+  void* cws = a.take(feature_center_workspace_bytes(D));
+  if (!g_packed || !group || !center || !cws) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  // the grouping (three tiny label-only kernels) runs on the side lane beside the centre and the feature packing
+  const bool centred = auto_center(metric, precision);
+  IEEE_REQUIRE(qf != nullptr, "retrieve: null pointer");
+  if (!centred) center = nullptr;
+  if ((rc = ieee_gallery_prepare(gf, ldg, dtype, G, D, metric, normalize, precision, g_pids, centred ? qf : nullptr, ldq, Q,
+                                 center, g_packed, group, cws, stream_)))
+    return rc;
   const size_t used = align256(a.off);
-  return ieee_retrieve_eval_prepared(qf, ldq, dtype, Q, D, metric, normalize, precision, g_packed, group, G, q_pids, q_camids,
+  return ieee_retrieve_eval_prepared(qf, ldq, dtype, Q, D, metric, normalize, precision, g_packed, group, center, G, q_pids, q_camids,
                                      g_camids, max_rank, cap, cap_host_out, distmat, ld, cmc, summary, per_query_ap,
                                      per_query_first, static_cast<uint8_t*>(workspace) + used, workspace_bytes - used, stream_);
 }

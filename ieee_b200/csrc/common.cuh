@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -34,11 +35,27 @@ const char* get_error();
     }                                      \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember what was set per device
+// (a process may evaluate on cuda:1 after cuda:0), one table per call site.
+#define IEEE_ENSURE_DYN_SMEM(kernel, bytes)                                                              \
+  do {                                                                                                   \
+    static std::atomic<size_t> ieee_smem_set_[64];                                                       \
+    int ieee_dev_ = -1;                                                                                  \
+    IEEE_CUDA_CHECK(cudaGetDevice(&ieee_dev_));                                                          \
+    const size_t ieee_need_ = (size_t)(bytes);                                                           \
+    if (ieee_need_ > 48 * 1024 &&                                                                        \
+        (ieee_dev_ < 0 || ieee_dev_ >= 64 || ieee_smem_set_[ieee_dev_].load(std::memory_order_relaxed) < ieee_need_)) { \
+      IEEE_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ieee_need_)); \
+      if (ieee_dev_ >= 0 && ieee_dev_ < 64) ieee_smem_set_[ieee_dev_].store(ieee_need_, std::memory_order_relaxed); \
+    }                                                                                                    \
+  } while (0)
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
 void count_launch(int n = 1);
 extern int g_debug_flags;       // ieee_set_debug_flags()
+extern int g_raster_panel;      // ieee_set_raster_panel(): m tiles per raster panel of the contraction (0 = sized for L2)
 extern int g_accum_chunk_kb;    // ieee_set_accum_chunk(): K-slices per tensor-core accumulation chunk (0 = whole K)   // bookkeeping behind ieee_launch_count()
 
 // ---- total order on float distances -----------------------------------------------------------------

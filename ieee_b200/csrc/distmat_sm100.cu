@@ -17,6 +17,7 @@
 // F16X3 (fp32-grade) mode runs three k-passes per 64-wide k block into the same accumulator:
 // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi); rows were scaled by powers of two when packed, undone by sq/sg here.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -60,10 +61,30 @@ struct GemmParams {
   int nseg;          // 1 (BF16) or 3 (F16X3)
   float alpha;       // -2 (euclidean) or -1 (cosine)
   int num_m_tiles, num_n_tiles;
+  int panel_m;       // m tiles per raster panel: the panel's A rows stay L2-resident while it sweeps all n tiles
   uint32_t idesc;    // tcgen05 instruction descriptor (operand format, M, N)
   int tma_store;     // 1: out is 16-byte aligned with a 16-byte-multiple pitch -> TMA store epilogue
   int debug;         // ieee_set_debug_flags()
+  // near-duplicate list (euclidean, chunked kernel): [0] = number of entries, [1 ..] = (row << 32 | first column) of every
+  // (row, 128-column span) holding an output with d < fix_tau * (|q|^2 + |g|^2); distmat_fixup_kernel recomputes those
+  // outputs in difference form.  May be null.
+  unsigned long long* fix_list;
+  uint32_t fix_cap;
+  float fix_tau;
 };
+
+// Tile order.  Inside a panel of `panel_m` m tiles, m runs fastest (the CTAs of one wave share B tiles in L2);
+// panels follow each other, so the A rows of a panel are fetched from HBM once however many n tiles there are
+// (a tall query block against a narrow gallery shard would otherwise stream all of A once per n tile).
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_blk, int& n_blk) {
+  const int per_panel = p.panel_m * p.num_n_tiles;
+  const int panel = t / per_panel;
+  const int r = t - panel * per_panel;
+  const int m0 = panel * p.panel_m;
+  const int pm = min(p.panel_m, p.num_m_tiles - m0);
+  n_blk = r / pm;
+  m_blk = m0 + (r - n_blk * pm);
+}
 
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -105,7 +126,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], CG * kEpilogueWarps * 32);
+      mbar_init(&tmem_empty_bar[i], CG * kEpilogueWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -127,7 +148,8 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int t = group_id; t < num_tiles; t += num_groups) {
-        const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+        int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
         const int row_a = (m_blk * CG + (int)cta_rank) * BLOCK_M;
         const int row_b = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < total_kb; ++kb) {
@@ -192,7 +214,8 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     float* col_sg = col_rg + BLOCK_N;                                        // [256]
     int it = 0;
     for (int t = group_id; t < num_tiles; t += num_groups, ++it) {
-      const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+      int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + ew * 32;   // first row of this warp
@@ -221,9 +244,12 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           tmem_ld_wait();
         }
         if (c == BLOCK_N / 32 - 1) {
-          // all of this thread's accumulator reads are done: hand the TMEM stage back to the MMA warp
+          // all of this warp's accumulator reads are done: hand the TMEM stage back to the MMA warp
           tc_fence_before();
-          if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          }
         }
         if (col_tile + c * 32 >= p.G || row0 >= p.Q || (p.debug & 1)) continue;   // warp-uniform
         if (p.tma_store) {
@@ -347,7 +373,7 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], CG * kEpiWarpsC * 32);
+      mbar_init(&tmem_empty_bar[i], CG * kEpiWarpsC);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -368,29 +394,37 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
       if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        const int total_kb = p.num_kb * p.nseg;
         for (int t = group_id; t < num_tiles; t += num_groups) {
-          const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+          int m_blk, n_blk;
+          tile_coords(p, t, m_blk, n_blk);
           const int row_a = (m_blk * CG + (int)cta_rank) * BLOCK_M;
           const int row_b = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
-          for (int kb = 0; kb < total_kb; ++kb) {
-            const int kk = kb / p.nseg, seg = kb - kk * p.nseg;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            const CUtensorMap* ma = (seg == 2) ? &tm_a_lo : &tm_a_hi;
-            const CUtensorMap* mb = (seg == 1) ? &tm_b_lo : &tm_b_hi;
-            void* sa = smem_a + stage * Cfg::kABytes;
-            void* sb = smem_b + stage * Cfg::kBBytes;
-            if constexpr (CG == 1) {
-              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_2d(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
-              tma_load_2d(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
-            } else {
-              if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              tma_load_2d_pair(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
-              tma_load_2d_pair(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
-              if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
+          for (int c = 0; c < num_chunks; ++c) {
+            const int k0 = c * chunk_kb, k1 = min(p.num_kb, k0 + chunk_kb);
+            // Inside a chunk the two cross terms (A_hi B_lo, A_lo B_hi: ~2^-11 of the main term) go first and the
+            // hi*hi products last: every tcgen05.mma truncates the running sum once, at the magnitude it has reached,
+            // so the only full-magnitude truncations left are the (k1 - k0) * 4 hi*hi instructions of the chunk.
+            for (int s = 0; s < p.nseg; ++s) {
+              const int seg = (p.nseg == 3) ? (s == 2 ? 0 : s + 1) : 0;
+              const CUtensorMap* ma = (seg == 2) ? &tm_a_lo : &tm_a_hi;
+              const CUtensorMap* mb = (seg == 1) ? &tm_b_lo : &tm_b_hi;
+              for (int kk = k0; kk < k1; ++kk) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                void* sa = smem_a + stage * Cfg::kABytes;
+                void* sb = smem_b + stage * Cfg::kBBytes;
+                if constexpr (CG == 1) {
+                  mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                  tma_load_2d(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+                  tma_load_2d(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+                } else {
+                  if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                  tma_load_2d_pair(ma, &full_bar[stage], sa, kk * BLOCK_K, row_a);
+                  tma_load_2d_pair(mb, &full_bar[stage], sb, kk * BLOCK_K, row_b);
+                  if (!is_leader) mbar_arrive_cluster(&full_bar[stage], 0);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -438,7 +472,8 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
     float* col_sg = col_rg + 128;                                            // [128]
     int ci = 0;
     for (int t = group_id; t < num_tiles; t += num_groups) {
-      const int m_blk = t % p.num_m_tiles, n_blk = t / p.num_m_tiles;
+      int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int col0 = n_blk * BLOCK_N + half * 128;
       const int my_row = row0 + lane;
@@ -472,9 +507,14 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
           }
         }
         tc_fence_before();
-        if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
       }
       if (row0 >= p.Q || (p.debug & 1)) continue;
+      const bool fix_on = p.fix_list != nullptr && p.rq != nullptr;
+      float viol = 0.f;                          // min over this thread's 128 outputs of d - fix_tau * (|q|^2 + |g|^2)
       // d = fma(coef * sg, sum, rq + rg), 16 columns at a time
 #pragma unroll
       for (int s16 = 0; s16 < 8; ++s16) {
@@ -482,10 +522,14 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
         if (cbase >= p.G) break;                 // warp-uniform
         auto out4 = [&](int k) {                 // outputs 4k .. 4k+3 of this 16-column group
           const int i = s16 * 16 + 4 * k;
-          return make_float4(__fmaf_rn(coef_row * col_sg[i], r[i], __fadd_rn(rq_row, col_rg[i])),
-                             __fmaf_rn(coef_row * col_sg[i + 1], r[i + 1], __fadd_rn(rq_row, col_rg[i + 1])),
-                             __fmaf_rn(coef_row * col_sg[i + 2], r[i + 2], __fadd_rn(rq_row, col_rg[i + 2])),
-                             __fmaf_rn(coef_row * col_sg[i + 3], r[i + 3], __fadd_rn(rq_row, col_rg[i + 3])));
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float base = __fadd_rn(rq_row, col_rg[i + j]);
+            o[j] = __fmaf_rn(coef_row * col_sg[i + j], r[i + j], base);
+            viol = fminf(viol, __fmaf_rn(-p.fix_tau, base, o[j]));    // < 0: a near-duplicate pair (see below)
+          }
+          return make_float4(o[0], o[1], o[2], o[3]);
         };
         if (p.tma_store) {
           if (lane == 0) tma_store_wait_read<0>();
@@ -519,6 +563,13 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
           }
         }
       }
+      // Near-duplicate pairs: almost all of |q|^2 + |g|^2 cancels, and what the truncating accumulator lost in the
+      // all-positive products is no longer small against d.  Rare: the (row, 128-column span) goes on a list and
+      // distmat_fixup_kernel recomputes the outputs below the bound in difference form.
+      if (fix_on && viol < 0.f && my_row < p.Q) {
+        const unsigned long long slot = atomicAdd(p.fix_list, 1ull);
+        if (slot < p.fix_cap) p.fix_list[1 + slot] = ((unsigned long long)(uint32_t)my_row << 32) | (uint32_t)col0;
+      }
     }
     if (p.tma_store && lane == 0) tma_store_wait<0>();
     __syncwarp();
@@ -527,6 +578,68 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// =====================================================================================================
+// Near-duplicate fix-up.  For a pair with |q - g|^2 << |q|^2 + |g|^2 the expansion |q|^2 + |g|^2 - 2 q.g keeps only
+// the absolute accuracy of its terms (the reference's fp32 GEMM has the same problem, distance.py:59-64: self
+// distances of +-3e-7 (|q|^2 + |g|^2)).  The chunked kernel lists the (row, 128-column span)s in which it saw an output
+// below fix_tau of its scale; one warp per entry re-reads that span of the block and recomputes every output below the
+// bound as sum_k (q_k - g_k)^2 from the packed planes -- exact operands (hi + lo is the packed value), fp32 FMA chain,
+// relative error ~1e-7 of d itself.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) distmat_fixup_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q_lo,
+                                                             const __half* __restrict__ g_hi, const __half* __restrict__ g_lo,
+                                                             const float* __restrict__ sq, const float* __restrict__ sg,
+                                                             const float* __restrict__ rq, const float* __restrict__ rg, int Dp,
+                                                             int G, float tau, const unsigned long long* __restrict__ list,
+                                                             uint32_t cap, float* __restrict__ out, int64_t ldo) {
+  const unsigned long long n64 = list[0];
+  const uint32_t n = n64 < cap ? (uint32_t)n64 : cap;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t e = warp; e < n; e += nwarps) {
+    // entry = (row, first column of a 128-column span) in which the contraction saw an output below the bound
+    const unsigned long long rc = list[1 + e];
+    const uint32_t row = (uint32_t)(rc >> 32), col0 = (uint32_t)rc;
+    const float a_s = sq[row], a_n = rq[row];
+    const uint4* ah = reinterpret_cast<const uint4*>(q_hi + (size_t)row * Dp);
+    const uint4* al = reinterpret_cast<const uint4*>(q_lo + (size_t)row * Dp);
+    for (int j0 = 0; j0 < 128; j0 += 32) {
+      const int colj = (int)col0 + j0 + lane;
+      bool hit = false;
+      if (colj < G) hit = out[(int64_t)row * ldo + colj] < tau * __fadd_rn(a_n, rg[colj]);
+      unsigned todo = __ballot_sync(0xffffffffu, hit);
+      while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t col = col0 + j0 + b;
+        const float b_s = sg[col];
+        const uint4* bh = reinterpret_cast<const uint4*>(g_hi + (size_t)col * Dp);
+        const uint4* bl = reinterpret_cast<const uint4*>(g_lo + (size_t)col * Dp);
+        float acc = 0.f;
+        for (int i = lane; i < Dp / 8; i += 32) {      // 8 halves per 16-byte load
+          const uint4 x0 = ah[i], x1 = al[i], y0 = bh[i], y1 = bl[i];
+          const __half2* xh = reinterpret_cast<const __half2*>(&x0);
+          const __half2* xl = reinterpret_cast<const __half2*>(&x1);
+          const __half2* yh = reinterpret_cast<const __half2*>(&y0);
+          const __half2* yl = reinterpret_cast<const __half2*>(&y1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a_hi = __half22float2(xh[j]), a_lo = __half22float2(xl[j]);
+            const float2 b_hi = __half22float2(yh[j]), b_lo = __half22float2(yl[j]);
+            const float d0 = __fsub_rn(__fadd_rn(a_hi.x, a_lo.x) * a_s, __fadd_rn(b_hi.x, b_lo.x) * b_s);
+            const float d1 = __fsub_rn(__fadd_rn(a_hi.y, a_lo.y) * a_s, __fadd_rn(b_hi.y, b_lo.y) * b_s);
+            acc = __fmaf_rn(d0, d0, acc);
+            acc = __fmaf_rn(d1, d1, acc);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[(int64_t)row * ldo + col] = acc;
+      }
+    }
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -569,26 +682,32 @@ static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const v
   return IEEE_OK;
 }
 
+// Operand tensor maps, epilogue terms and tile raster shared by both kernels.
+struct GemmLaunch {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
+  GemmParams p;
+  int groups;
+};
+
 template <int CG>
-static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
-                       int precision, float* out, int64_t ldo, cudaStream_t stream) {
-  using Cfg = GemmCfg<CG>;
+static int gemm_setup(GemmLaunch& L, const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                      int precision, float* out, int64_t ldo, int out_box_cols, CUtensorMapSwizzle out_swizzle) {
+  constexpr int kBRows = BLOCK_N / CG;
   PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
   const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
   const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
   const CUtensorMapDataType dt16 = CU_TENSOR_MAP_DATA_TYPE_UINT16;   // the copy engine only moves 16-bit words
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
   int rc;
-  if ((rc = make_tmap(&ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&L.ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&L.tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, kBRows, BLOCK_K))) return rc;
   if (precision == IEEE_PREC_F16X3) {
-    if ((rc = make_tmap(&ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
+    if ((rc = make_tmap(&L.ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = make_tmap(&L.tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, kBRows, BLOCK_K))) return rc;
   } else {
-    ta_lo = ta_hi;
-    tb_lo = tb_hi;
+    L.ta_lo = L.ta_hi;
+    L.tb_lo = L.tb_hi;
   }
-  GemmParams p;
+  GemmParams& p = L.p;
   const bool euclid = metric == IEEE_METRIC_EUCLIDEAN;
   p.rq = euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr;
   p.rg = euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr;
@@ -603,115 +722,109 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   p.nseg = precision == IEEE_PREC_F16X3 ? 3 : 1;
   p.num_m_tiles = (int)((Q + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
+  // raster panel: as many m tiles as keep the panel's A planes within ~40 MB of the 126 MB L2
+  const double a_tile_bytes = double(BLOCK_M * CG) * double(lq.Dp) * 2.0 * (precision == IEEE_PREC_F16X3 ? 2.0 : 1.0);
+  int panel = (int)(40.0 * 1024 * 1024 / a_tile_bytes);
+  if (g_raster_panel > 0) panel = g_raster_panel;
+  p.panel_m = panel < 1 ? 1 : (panel > p.num_m_tiles ? p.num_m_tiles : panel);
   p.idesc = umma_idesc_16bit(BLOCK_M * CG, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
   p.debug = g_debug_flags;
+  p.fix_list = nullptr;
+  p.fix_cap = 0;
+  p.fix_tau = 0.f;
   p.tma_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 && !(g_debug_flags & 4)) ? 1 : 0;
   if (p.tma_store) {
-    if ((rc = make_tmap(&t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, Q, G, ldo, 32, 32))) return rc;
+    if ((rc = make_tmap(&L.t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, Q, G, ldo, 32, out_box_cols, out_swizzle))) return rc;
   } else {
-    t_out = ta_hi;
+    L.t_out = L.ta_hi;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  int groups = sm_count() / CG;
-  if (groups > num_tiles) groups = num_tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  L.groups = sm_count() / CG;
+  if (L.groups > num_tiles) L.groups = num_tiles;
+  return IEEE_OK;
+}
+
+static void cluster_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int threads, size_t smem,
+                                  int cluster, cudaStream_t stream) {
+  cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, t_out, p));
+}
+
+template <int CG>
+static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                       int precision, float* out, int64_t ldo, cudaStream_t stream) {
+  using Cfg = GemmCfg<CG>;
+  GemmLaunch L;
+  int rc = gemm_setup<CG>(L, q_packed, Q, g_packed, G, D, metric, precision, out, ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  IEEE_ENSURE_DYN_SMEM(distmat_umma_kernel<CG>, Cfg::kSmemBytes);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_launch_config(cfg, attr, L.groups * CG, kThreads, Cfg::kSmemBytes, CG, stream);
+  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, L.ta_hi, L.ta_lo, L.tb_hi, L.tb_lo, L.t_out, L.p));
   count_launch();
   return IEEE_OK;
 }
 
+// pairs below 2^-6 of their scale are recomputed: above it, what the accumulator can lose (<= ~1.3e-6 of the scale
+// at the default chunking, all-positive products) stays under 1e-4 of the distance itself
+constexpr float kFixTau = 0.015625f;
+
+size_t distmat_fixup_bytes(int64_t Q) { return align256((size_t(2 * Q + 4096) + 2) * 8); }
+
 template <int CG>
 static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
-                               int precision, float* out, int64_t ldo, cudaStream_t stream, int chunk_kb) {
+                               int precision, float* out, int64_t ldo, cudaStream_t stream, int chunk_kb, void* fix_ws) {
   using Cfg = GemmCfgC<CG>;
-  PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
-  const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
-  const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
-  const CUtensorMapDataType dt16 = CU_TENSOR_MAP_DATA_TYPE_UINT16;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, t_out;
-  int rc;
-  if ((rc = make_tmap(&ta_hi, dt16, 2, qb + lq.hi_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&tb_hi, dt16, 2, gb + lg.hi_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
-  if (precision == IEEE_PREC_F16X3) {
-    if ((rc = make_tmap(&ta_lo, dt16, 2, qb + lq.lo_off, Q, lq.Dp, lq.Dp, BLOCK_M, BLOCK_K))) return rc;
-    if ((rc = make_tmap(&tb_lo, dt16, 2, gb + lg.lo_off, G, lg.Dp, lg.Dp, Cfg::kBRows, BLOCK_K))) return rc;
-  } else {
-    ta_lo = ta_hi;
-    tb_lo = tb_hi;
+  GemmLaunch L;
+  int rc = gemm_setup<CG>(L, q_packed, Q, g_packed, G, D, metric, precision, out, ldo, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  const bool fix = fix_ws != nullptr && metric == IEEE_METRIC_EUCLIDEAN && precision == IEEE_PREC_F16X3 && !(g_debug_flags & 32);
+  if (fix) {
+    L.p.fix_list = static_cast<unsigned long long*>(fix_ws);
+    L.p.fix_cap = (uint32_t)(2 * Q + 4096);
+    L.p.fix_tau = kFixTau;
+    IEEE_CUDA_CHECK(cudaMemsetAsync(fix_ws, 0, 8, stream));
   }
-  GemmParams p;
-  const bool euclid = metric == IEEE_METRIC_EUCLIDEAN;
-  p.rq = euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr;
-  p.rg = euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr;
-  p.sq = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(qb + lq.scale_off) : nullptr;
-  p.sg = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(gb + lg.scale_off) : nullptr;
-  p.alpha = euclid ? -2.0f : -1.0f;
-  p.out = out;
-  p.ldo = ldo;
-  p.Q = (int)Q;
-  p.G = (int)G;
-  p.num_kb = (int)(lq.Dp / BLOCK_K);
-  p.nseg = precision == IEEE_PREC_F16X3 ? 3 : 1;
-  p.num_m_tiles = (int)((Q + BLOCK_M * CG - 1) / (BLOCK_M * CG));
-  p.num_n_tiles = (int)((G + BLOCK_N - 1) / BLOCK_N);
-  p.idesc = umma_idesc_16bit(BLOCK_M * CG, BLOCK_N, precision == IEEE_PREC_F16X3 ? 0u : 1u);
-  p.debug = g_debug_flags;
-  p.tma_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 && !(g_debug_flags & 4)) ? 1 : 0;
-  if (p.tma_store) {
-    if ((rc = make_tmap(&t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, Q, G, ldo, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  } else {
-    t_out = ta_hi;
-  }
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  int groups = sm_count() / CG;
-  if (groups > num_tiles) groups = num_tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(distmat_umma_chunked_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(kThreadsC);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
+  IEEE_ENSURE_DYN_SMEM(distmat_umma_chunked_kernel<CG>, Cfg::kSmemBytes);
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_chunked_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, t_out, p, chunk_kb));
+  cluster_launch_config(cfg, attr, L.groups * CG, kThreadsC, Cfg::kSmemBytes, CG, stream);
+  IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_chunked_kernel<CG>, L.ta_hi, L.ta_lo, L.tb_hi, L.tb_lo, L.t_out, L.p,
+                                     chunk_kb));
   count_launch();
+  if (fix) {
+    PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
+    const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
+    const uint8_t* gb = static_cast<const uint8_t*>(g_packed);
+    distmat_fixup_kernel<<<sm_count(), 256, 0, stream>>>(
+        reinterpret_cast<const __half*>(qb + lq.hi_off), reinterpret_cast<const __half*>(qb + lq.lo_off),
+        reinterpret_cast<const __half*>(gb + lg.hi_off), reinterpret_cast<const __half*>(gb + lg.lo_off),
+        reinterpret_cast<const float*>(qb + lq.scale_off), reinterpret_cast<const float*>(gb + lg.scale_off),
+        reinterpret_cast<const float*>(qb + lq.norm_off), reinterpret_cast<const float*>(gb + lg.norm_off), (int)lq.Dp, (int)G,
+        kFixTau, L.p.fix_list, L.p.fix_cap, out, ldo);
+    count_launch();
+    IEEE_CUDA_CHECK(cudaGetLastError());
+  }
   return IEEE_OK;
 }
 
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
-                 float* out, int64_t ldo, cudaStream_t stream, int cta_group) {
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws) {
   // chunked accumulation serves the fp32-grade mode; the 1-pass BF16 mode keeps the whole K in TMEM (throughput mode)
   if (g_accum_chunk_kb > 0 && (precision == IEEE_PREC_F16X3 || (g_debug_flags & 8))) {
     if (cta_group == 2)
-      return launch_umma_chunked<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
-    return launch_umma_chunked<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb);
+      return launch_umma_chunked<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws);
+    return launch_umma_chunked<1>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws);
   }
   if (cta_group == 2)
     return launch_umma<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);

@@ -49,39 +49,57 @@ __device__ __forceinline__ float warp_max(float v) {
 // fp16's 65504), then hi = fp16(y), lo = fp16(y - hi): 22 mantissa bits survive, and lo (~2^-12 |y|) stays a
 // NORMAL fp16 number for every element within 2^-16 of the row maximum.  The contraction's epilogue multiplies
 // by 2^(e_q - 14) * 2^(e_g - 14).
+//
+// center (may be null): a D-vector c subtracted from every (normalised) row before it is split.  The squared
+// euclidean distance is translation invariant, |q - g|^2 = |(q - c) - (g - c)|^2, but its fp32 evaluation
+// |q|^2 + |g|^2 - 2 q.g is not: the cancellation error scales with |q|^2 + |g|^2, and post-ReLU features (all
+// non-negative, ieee3modalPart.py:417) share a large common component.  Subtracting it shrinks the row terms to the
+// spread of the data and makes the products mixed-sign, so the tensor core's truncating accumulator no longer
+// drifts one way.  Zero padding beyond D stays zero.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
-                                                         int n_norm, int mode, uint16_t* __restrict__ hi,
-                                                         uint16_t* __restrict__ lo, float* __restrict__ f32,
-                                                         float* __restrict__ norms, float* __restrict__ row_scale) {
+                                                         int n_norm, int mode, const float* __restrict__ center,
+                                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                         float* __restrict__ f32, float* __restrict__ norms,
+                                                         float* __restrict__ row_scale) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* xr = x + row * ld;
   float den[2] = {1.0f, 1.0f};
   float amax = 0.f;
-  if (n_norm > 0 || mode == PACK_F16_HILO) {
-    for (int pass = 0; pass < (n_norm > 0 ? n_norm : 1); ++pass) {
-      float s = 0.f;
+  for (int pass = 0; pass < n_norm; ++pass) {   // the reference's F.normalize calls, one row reduction each
+    float s = 0.f;
 #pragma unroll 6
-      for (int i = lane * VEC; i < D; i += 32 * VEC) {
-        float v[VEC];
-        RowLoader<T, VEC>::load(xr, i, v);
+    for (int i = lane * VEC; i < D; i += 32 * VEC) {
+      float v[VEC];
+      RowLoader<T, VEC>::load(xr, i, v);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float t = v[j];
-          if (pass == 0) amax = fmaxf(amax, fabsf(t));
-          if (pass == 1) t = __fdiv_rn(t, den[0]);
-          s = __fmaf_rn(t, t, s);
-        }
+      for (int j = 0; j < VEC; ++j) {
+        float t = v[j];
+        if (pass == 1) t = __fdiv_rn(t, den[0]);
+        s = __fmaf_rn(t, t, s);
       }
-      s = warp_sum(s);
-      if (pass < n_norm) den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);  // F.normalize: clamp_min(norm, eps)
+    }
+    s = warp_sum(s);
+    den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);  // F.normalize: clamp_min(norm, eps)
+  }
+  if (mode == PACK_F16_HILO) {                  // largest magnitude of the row as the contraction will see it
+#pragma unroll 6
+    for (int i = lane * VEC; i < D; i += 32 * VEC) {
+      float v[VEC], c[VEC];
+      RowLoader<T, VEC>::load(xr, i, v);
+      if (center != nullptr) RowLoader<float, VEC>::load(center, i, c);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float t = v[j];
+        if (n_norm >= 1) t = __fdiv_rn(t, den[0]);
+        if (n_norm >= 2) t = __fdiv_rn(t, den[1]);
+        if (center != nullptr) t = __fsub_rn(t, c[j]);
+        amax = fmaxf(amax, fabsf(t));
+      }
     }
     amax = warp_max(amax);
-    // division by a positive constant is monotone, so the maximum of the normalised row is the normalised maximum
-    if (n_norm >= 1) amax = __fdiv_rn(amax, den[0]);
-    if (n_norm >= 2) amax = __fdiv_rn(amax, den[1]);
   }
   int e = 0;
   if (mode == PACK_F16_HILO && amax > 0.f && amax < 3.0e38f) {
@@ -92,12 +110,12 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   float sq = 0.f;
 #pragma unroll 6
   for (int i = lane * VEC; i < Dp; i += 32 * VEC) {
-    float v[VEC];
+    float v[VEC], c[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { v[j] = 0.f; c[j] = 0.f; }
     if (i < D) {
       RowLoader<T, VEC>::load(xr, i, v);  // D % VEC == 0 on the vector path
-    } else {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] = 0.f;
+      if (center != nullptr) RowLoader<float, VEC>::load(center, i, c);
     }
     uint16_t h[VEC], l[VEC];
 #pragma unroll
@@ -105,6 +123,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
       float t = v[j];
       if (n_norm >= 1) t = __fdiv_rn(t, den[0]);
       if (n_norm >= 2) t = __fdiv_rn(t, den[1]);
+      t = __fsub_rn(t, c[j]);
       float u = t;   // the value whose square enters the row term: what the contraction actually multiplies
       if (mode == PACK_BF16) {
         const __nv_bfloat16 b = __float2bfloat16_rn(t);
@@ -142,7 +161,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
 }
 
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
-                  void* packed, cudaStream_t stream) {
+                  const float* center, void* packed, cudaStream_t stream) {
   IEEE_REQUIRE(x != nullptr && packed != nullptr, "pack_features: null pointer");
   IEEE_REQUIRE(rows >= 0 && D > 0 && ld >= D, "pack_features: bad shape rows=%lld D=%lld ld=%lld", (long long)rows,
                (long long)D, (long long)ld);
@@ -150,6 +169,9 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
   IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "pack_features: unknown dtype %d", dtype);
   IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
   IEEE_REQUIRE(precision >= IEEE_PREC_F16X3 && precision <= IEEE_PREC_FP32_SIMT, "unknown precision %d", precision);
+  IEEE_REQUIRE(center == nullptr || metric == IEEE_METRIC_EUCLIDEAN,
+               "pack_features: a centre only applies to the euclidean metric (cosine is not translation invariant)");
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(center) & 15) == 0, "pack_features: centre must be 16-byte aligned");
   if (rows == 0) return IEEE_OK;
   PackedLayout L = packed_layout(rows, D, precision);
   uint8_t* base = static_cast<uint8_t*>(packed);
@@ -167,14 +189,97 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
     const float* xf = static_cast<const float*>(x);
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xf) & 15) == 0);
     if (vec)
-      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
+      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
     else
-      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
+      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
   } else {
     pack_rows_kernel<__nv_bfloat16, 1><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, (int)D,
-                                                                   (int)L.Dp, n_norm, mode, hi, lo, f32, norms, rscale);
+                                                                   (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
   }
   count_launch();
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Centre of a feature set: the column mean over up to `max_rows` evenly strided sample rows (deterministic:
+// fixed assignment of rows to warps, fixed summation order).  ANY vector is a valid centre -- it only has to be
+// the same for both operands of a contraction -- so a sample is enough, and for normalised features the mean of
+// the raw rows is simply scaled to unit length (m / max(|m|, 1e-12)) instead of normalising every sample row.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCenterGroups = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) center_partial_kernel(const T* __restrict__ x, int64_t ld, int64_t stride, int n_s, int D,
+                                                              float* __restrict__ partial) {
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.y;
+  const int col0 = blockIdx.x * 128 + lane * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = g + kCenterGroups * w; i < n_s; i += kCenterGroups * 8) {
+    const T* xr = x + (int64_t)i * stride * ld;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j < D) acc[j] += static_cast<float>(xr[col0 + j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[w][lane * 4 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col < D) partial[(int64_t)g * D + col] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) center_finish_kernel(const float* __restrict__ partial, int n_s, int D, int unit,
+                                                              float* __restrict__ center) {
+  __shared__ float red[32];
+  __shared__ float scale_s;
+  float sq = 0.f;
+  const float inv = 1.0f / (float)n_s;
+  for (int col = threadIdx.x; col < D; col += 1024) {
+    float s = 0.f;
+    for (int g = 0; g < kCenterGroups; ++g) s += partial[(int64_t)g * D + col];
+    s *= inv;
+    center[col] = s;
+    sq = __fmaf_rn(s, s, sq);
+  }
+  if (!unit) return;
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = warp_sum(red[threadIdx.x]);
+    if (threadIdx.x == 0) scale_s = 1.0f / fmaxf(__fsqrt_rn(t), 1e-12f);
+  }
+  __syncthreads();
+  const float sc = scale_s;
+  for (int col = threadIdx.x; col < D; col += 1024) center[col] *= sc;
+}
+
+size_t feature_center_workspace_bytes(int64_t D) { return align256(size_t(kCenterGroups) * size_t(D) * 4); }
+
+int feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
+                   float* center, void* workspace, cudaStream_t stream) {
+  IEEE_REQUIRE(x && center && workspace, "feature_center: null pointer");
+  IEEE_REQUIRE(rows > 0 && D > 0 && ld >= D && D <= (1 << 24), "feature_center: bad shape rows=%lld D=%lld ld=%lld",
+               (long long)rows, (long long)D, (long long)ld);
+  IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "feature_center: unknown dtype %d", dtype);
+  if (max_rows <= 0) max_rows = 512;
+  const int n_s = (int)(rows < max_rows ? rows : max_rows);
+  const int64_t stride = rows / n_s;
+  float* partial = static_cast<float*>(workspace);
+  dim3 grid((unsigned)((D + 127) / 128), kCenterGroups);
+  if (dtype == IEEE_DTYPE_F32)
+    center_partial_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, stride, n_s, (int)D, partial);
+  else
+    center_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, stride, n_s, (int)D, partial);
+  center_finish_kernel<<<1, 1024, 0, stream>>>(partial, n_s, (int)D, normalize ? 1 : 0, center);
+  count_launch(2);
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }

@@ -281,10 +281,11 @@ __device__ __forceinline__ void count_bump(CountCtx& c, int b, int delta) {
 }
 
 // Cell of a distance in the guarded table (L = c.L live cells): index 0 = "before every threshold" (bin 0), 1 .. L = the L cells over
-// [lo, hi], L + 1 = "after every threshold" (trash bin).  floor() sends d < lo below 0 and d >> hi beyond L; NaN
-// converts to 0 and lands in cell 1, which holds T_0 and therefore takes the exact path (key order: last).
+// [lo, hi], L + 1 = "after every threshold" (trash bin).  floor() sends d < lo below 0 and d >> hi beyond L; fminf
+// returns its non-NaN operand, so a NaN distance goes to the trash guard: NaN ranks after every (finite) threshold,
+// as in NumPy's sort (the table is only used when all thresholds are finite).
 __device__ __forceinline__ uint32_t count_cell(const CountCtx& c, float d) {
-  int ci = __float2int_rd((d - c.lo) * c.scale);
+  int ci = __float2int_rd(fminf((d - c.lo) * c.scale, (float)c.L));
   ci = max(min(ci, c.L) + 1, 0);
   return c.cell[ci];
 }
@@ -878,11 +879,8 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
     const bool team = G > count_warp_max_g();      // long rows: the whole CTA streams one query
     const size_t wsmem = team ? size_t(warp_smem_per_query(rmax, kWarpQ)) : size_t(kWarpQ) * warp_smem_per_query(rmax, 1);
     auto kern = team ? rank_count_warp_kernel<kWarpQ> : rank_count_warp_kernel<1>;
-    static size_t wattr[2] = {0, 0};
-    if (wsmem > 48 * 1024 && wsmem > wattr[team]) {
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      wattr[team] = wsmem;
-    }
+    if (team) IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<kWarpQ>, wsmem);
+    else IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<1>, wsmem);
     const unsigned grid = team ? (unsigned)Q : (unsigned)((Q + kWarpQ - 1) / kWarpQ);
     kern<<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel,
                                                junk, n_junk, counts, ties);
@@ -893,11 +891,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   const int Rp = next_pow2(max(out_cap, 2));
   const size_t smem = count_smem_plan(Rp).total;
   IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: %d relevant items per query exceed the shared-memory budget", out_cap);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  IEEE_ENSURE_DYN_SMEM(rank_count_kernel, smem);
   rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, Rp, rel_all,
                                                                   n_rel, junk, n_junk, counts, ties);
   count_launch();
@@ -1035,8 +1029,7 @@ int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_lis
   IEEE_REQUIRE(ap && first && short_list && cmc && summary, "rank_reduce: null pointer");
   IEEE_REQUIRE(Q > 0 && max_rank >= 1 && max_rank <= 8192, "rank_reduce: bad shape (max_rank=%d)", max_rank);
   const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
-  if (smem > 48 * 1024)
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(rank_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IEEE_ENSURE_DYN_SMEM(rank_reduce_kernel, smem);
   rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, overflow); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -1244,11 +1237,7 @@ int topk_merge(const int32_t* idx_all, const float* val_all, int32_t shards, int
   IEEE_REQUIRE(np <= 16384, "topk_merge: shards*k=%d too large", shards * k);
   if (Q == 0) return IEEE_OK;
   const size_t smem = size_t(np) * 8;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    IEEE_CUDA_CHECK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  IEEE_ENSURE_DYN_SMEM(topk_merge_kernel, smem);
   topk_merge_kernel<<<(unsigned)Q, 256, smem, stream>>>(idx_all, val_all, shards, Q, k, np, idx, val); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;

@@ -450,11 +450,7 @@ int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, con
   // K3
   {
     const size_t smem = size_t(kRowWarps) * (p.k1p + p.khp + p.cap_v_pow2) * 4;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rr_krecip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
+    IEEE_ENSURE_DYN_SMEM(rr_krecip_kernel, smem);
     rr_krecip_kernel<<<(N + kRowWarps - 1) / kRowWarps, 32 * kRowWarps, smem, stream>>>(rank, p.k1p, orig, N, p.k1p, p.khp,
                                                                                          p.cap_v, p.cap_v_pow2, vcol, vval, vcnt);
     count_launch();
@@ -466,11 +462,7 @@ int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, con
   int fcap = p.cap_v;
   if (k2 != 1) {
     const size_t smem = size_t(p.cap_e_pow2) * 8;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      IEEE_CUDA_CHECK(cudaFuncSetAttribute(rr_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
+    IEEE_ENSURE_DYN_SMEM(rr_expand_kernel, smem);
     rr_expand_kernel<<<N, 256, smem, stream>>>(rank, p.k1p, N, k2, p.cap_v, vcol, vval, vcnt, p.cap_e, p.cap_e_pow2, ecol, eval, ecnt);
     count_launch();
     fcol = ecol; fval = eval; fcnt = ecnt; fcap = p.cap_e;

@@ -59,6 +59,24 @@ TRACE = Trace()
 # query.  It is a hint, not a trusted value: the gather kernel flags any list that does not fit, and evaluate()
 # then recomputes the capacity and runs again.
 _CAP_MEMO = {}
+# The key is built from tensor identities (address, size, version counter), so every entry also KEEPS its key
+# tensors alive: a freed label tensor whose address is reused by another tensor of the same size could otherwise
+# produce a false hit -- harmless on one GPU (the overflow flag catches it), but with several ranks a hit on one
+# rank and a miss on another would make them issue different collectives.
+_CAP_MEMO_REFS = {}
+
+
+def _memo_put(key, value, refs):
+    if len(_CAP_MEMO) > 64:
+        _CAP_MEMO.clear()
+        _CAP_MEMO_REFS.clear()
+    _CAP_MEMO[key] = value
+    _CAP_MEMO_REFS[key] = refs
+
+
+def _memo_drop(key):
+    _CAP_MEMO.pop(key, None)
+    _CAP_MEMO_REFS.pop(key, None)
 
 
 _STAGE_POOL = {}
@@ -117,28 +135,81 @@ def shard_bounds(num_rows: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def centering_applies(metric: str, precision: str) -> bool:
+    """Euclidean operands are packed relative to a common centre (ieee_pack_features); cosine is not translation
+    invariant and the 1-pass bf16 mode multiplies bf16 inputs exactly as they are."""
+    return metric == "euclidean" and precision != "bf16" and _lib.load().ieee_set_centering(-1) != 0
+
+
+def feature_center(feats: torch.Tensor, normalize: bool = False, max_rows: int = 0) -> torch.Tensor:
+    """Column mean over a strided sample of the rows (unit length when the rows will be normalised): float32 [D] on
+    the device, deterministic (ieee_feature_center)."""
+    assert feats.is_cuda and feats.dim() == 2 and feats.dtype in _lib.DTYPES and feats.shape[0] > 0
+    if feats.stride(1) != 1:
+        feats = feats.contiguous()
+    rows, D = feats.shape
+    lib = _lib.load()
+    center = torch.empty(D, dtype=torch.float32, device=feats.device)
+    ws = torch.empty(lib.ieee_feature_center_workspace_bytes(D), dtype=torch.uint8, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.call("ieee_feature_center", feats.data_ptr(), _lib.DTYPES[feats.dtype], feats.stride(0), rows, D, int(normalize),
+                  max_rows, center.data_ptr(), ws.data_ptr(), _lib.stream())
+    return center
+
+
 class PackedFeatures:
     """Feature rows in the operand layout of the tensor-core kernel (ieee_pack_features)."""
 
-    def __init__(self, feats: torch.Tensor, metric: str, normalize: bool, precision: str):
-        assert feats.is_cuda and feats.dim() == 2 and feats.dtype in _lib.DTYPES
+    def __init__(self, feats: torch.Tensor, metric: str, normalize: bool, precision: str, center: torch.Tensor | None = None):
+        if not (feats.is_cuda and feats.dim() == 2):
+            raise TypeError("PackedFeatures: expected a 2-D CUDA tensor")
+        if feats.dtype not in _lib.DTYPES:
+            raise TypeError("PackedFeatures: features must be float32 or bfloat16, got {}".format(feats.dtype))
         if feats.stride(1) != 1:
             feats = feats.contiguous()
         self.rows, self.D = feats.shape
         self.metric, self.precision = _lib.METRICS[metric], _lib.PRECISIONS[precision]
+        self.center = center
         lib = _lib.load()
         self.buf = torch.empty(max(lib.ieee_packed_bytes(self.rows, self.D, self.precision), 256), dtype=torch.uint8,
                                device=feats.device)
         if self.rows:
             _lib.call("ieee_pack_features", feats.data_ptr(), _lib.DTYPES[feats.dtype], feats.stride(0), self.rows, self.D,
-                      self.metric, int(normalize), self.precision, self.buf.data_ptr(), _lib.stream())
+                      self.metric, int(normalize), self.precision, _lib.ptr(center), self.buf.data_ptr(), _lib.stream())
 
 
 def packed_distmat(q: PackedFeatures, g: PackedFeatures, out: torch.Tensor) -> torch.Tensor:
     assert q.D == g.D and q.metric == g.metric and q.precision == g.precision
+    assert _lib.ptr(q.center) == _lib.ptr(g.center), "both operands must be packed with the same centre"
     _lib.call("ieee_distmat_packed", q.buf.data_ptr(), q.rows, g.buf.data_ptr(), g.rows, q.D, q.metric, q.precision,
-              out.data_ptr(), out.stride(0), _lib.stream())
+              out.data_ptr(), out.stride(0), _fixup_workspace(q.rows, out.device).data_ptr(), _lib.stream())
     return out
+
+
+_FIXUP_WS = {}
+
+
+def _fixup_workspace(rows: int, device) -> torch.Tensor:
+    """Near-duplicate list of the contraction (ieee_distmat_fixup_bytes): one per device and stream, grown on demand;
+    contractions on one stream run one after the other, so they can share it."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    need = _lib.load().ieee_distmat_fixup_bytes(rows)
+    ws = _FIXUP_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _FIXUP_WS[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+    return ws
+
+
+def _as_features(t: torch.Tensor) -> torch.Tensor:
+    """float32 / bfloat16 features pass through; float16 (AMP extraction) and float64 are computed in float32, as
+    compute_distance_matrix does -- there is no float64 contraction and no gradient on this path."""
+    if not isinstance(t, torch.Tensor) or t.dim() != 2:
+        raise TypeError("features must be a 2-D torch.Tensor")
+    if t.dtype in _lib.DTYPES:
+        return t.detach()
+    if t.dtype in (torch.float16, torch.float64):
+        return t.detach().float()
+    raise TypeError("features must be a floating point tensor, got {}".format(t.dtype))
 
 
 class RetrievalEvaluator:
@@ -150,7 +221,7 @@ class RetrievalEvaluator:
 
     def __init__(self, gf: torch.Tensor, g_pids, g_camids, dist_metric: str = "euclidean", normalize_feature: bool = False,
                  precision: str | None = None, max_rank: int = 20, group=None, g_offset: int = 0, g_total: int | None = None,
-                 block_bytes: int = DEFAULT_BLOCK_BYTES):
+                 block_bytes: int = DEFAULT_BLOCK_BYTES, center: torch.Tensor | None = None):
         _lib.require_cuda()
         if dist_metric not in _lib.METRICS:
             raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(dist_metric))
@@ -162,27 +233,139 @@ class RetrievalEvaluator:
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.g_offset = g_offset
         self.block_bytes = block_bytes
+        if gf is not None:
+            gf = _as_features(gf)
+        # Euclidean operands are packed relative to a common centre (PackedFeatures).  It is taken from the QUERY set:
+        # queries are replicated on every rank of a sharded gallery, so all shards -- and a single-GPU evaluation of
+        # the same queries -- derive the same vector without exchanging anything.  The gallery is therefore packed
+        # on the first evaluate(), or here when the caller hands a centre in.
+        self._use_center = centering_applies(dist_metric, self.precision)
+        self.center = center
+        self._gallery_dev = gf
+        # the gallery as packed row chunks [(first row, PackedFeatures)]: one chunk when the features are already
+        # in HBM, several when they are streamed from the host (from_host) so that the contraction of chunk i
+        # overlaps the PCIe copy of chunk i + 1
+        self.chunks = []
         with torch.cuda.device(self.device):
-            # the gallery as packed row chunks [(first row, PackedFeatures)]: one chunk when the features are already
-            # in HBM, several when they are streamed from the host (from_host) so that the contraction of chunk i
-            # overlaps the PCIe copy of chunk i + 1
-            # the big kernel first: the host work below (label copies, grouping on the side stream) then runs while
-            # the GPU packs, instead of in front of an idle GPU
-            self.chunks = [(0, PackedFeatures(gf, dist_metric, normalize_feature, self.precision))] if gf is not None else []
-            # grouping: three tiny kernels behind the pack on the same stream (a side stream costs more host time than
-            # they take; the capacity query, when one is needed, still runs beside the contraction: list_cap_async)
-            self.labels = GalleryLabels(g_pids, g_camids, self.device)
+            # a device-resident gallery is prepared by ONE foreign call (grouping on a side stream beside centre + pack):
+            # here when no centre is needed or one was handed in, else in the first evaluate()
+            self.labels = GalleryLabels(g_pids, g_camids, self.device, build=gf is None)
+            if gf is not None and (not self._use_center or center is not None):
+                self._prepare_gallery(None)
         self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
         self._copy = None
         self._host_gallery = None
         self._label_keys = (_tensor_key(g_pids), _tensor_key(g_camids))
+        self._label_refs = (g_pids, g_camids)
+
+    def _prepare_gallery(self, qf_dev):
+        """ieee_gallery_prepare: grouping + [centre from the query rows] + packing of a device-resident gallery."""
+        gf = self._gallery_dev
+        if gf.stride(1) != 1:
+            gf = self._gallery_dev = gf.contiguous()
+        G, D = gf.shape
+        lib = _lib.load()
+        prec = _lib.PRECISIONS[self.precision]
+        pk = PackedFeatures.__new__(PackedFeatures)
+        pk.rows, pk.D, pk.metric, pk.precision = G, D, _lib.METRICS[self.metric], prec
+        pk.buf = torch.empty(max(lib.ieee_packed_bytes(G, D, prec), 256), dtype=torch.uint8, device=self.device)
+        src = None
+        if self._use_center and self.center is None:
+            src = qf_dev if qf_dev.stride(1) == 1 else qf_dev.contiguous()
+            assert src.dtype == gf.dtype, "query and gallery features must have the same dtype"
+            self.center = torch.empty(D, dtype=torch.float32, device=self.device)
+            ws = torch.empty(lib.ieee_gallery_prepare_workspace_bytes(D), dtype=torch.uint8, device=self.device)
+        pk.center = self.center
+        cur = torch.cuda.current_stream()
+        _lib.call("ieee_gallery_prepare", gf.data_ptr(), gf.stride(0), _lib.DTYPES[gf.dtype], G, D, pk.metric, int(self.normalize),
+                  prec, self.labels.pids.data_ptr(), _lib.ptr(src), src.stride(0) if src is not None else 0,
+                  src.shape[0] if src is not None else 0, _lib.ptr(self.center), pk.buf.data_ptr(),
+                  self.labels.group.data_ptr(), ws.data_ptr() if src is not None else None, cur.cuda_stream)
+        self.labels.ready = cur.record_event()
+        self.chunks = [(0, pk)]
+
+    def _ensure_center(self, qf_dev: torch.Tensor):
+        """Fix the centre (first query set seen) and prepare a device-resident gallery with it."""
+        if self._gallery_dev is not None and not self.chunks:
+            self._prepare_gallery(qf_dev)
+        elif self._use_center and self.center is None:
+            self.center = feature_center(qf_dev, self.normalize)
 
     # -- one query block ---------------------------------------------------------------------------------
     def _block_rows(self, Q: int) -> int:
         rows = max(128, int(self.block_bytes // (4 * max(self.G, 1))) // 128 * 128)
         return min(Q, rows)
+
+    def _ensure_block(self, rows: int):
+        if self._block is None or self._block.shape[0] < rows:
+            # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
+            # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
+            pitch = (self.G + 31) // 32 * 32
+            self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
+
+    def _distance_block(self, qpk: PackedFeatures) -> torch.Tensor:
+        """Distances of one packed query block against this rank's gallery rows, into the scratch block."""
+        out = self._block[: qpk.rows]
+        for i, (c0, gpk) in enumerate(self.chunks):
+            if isinstance(gpk, tuple):            # (event, host->device staging tensor): pack on arrival
+                ev, staged = gpk
+                torch.cuda.current_stream().wait_event(ev)
+                gpk = PackedFeatures(staged, self.metric, self.normalize, self.precision, self.center)
+                self.chunks[i] = (c0, gpk)        # packed once, reused by later query blocks
+            packed_distmat(qpk, gpk, out[:, c0: c0 + gpk.rows])
+            TRACE.mark("  chunk %d contraction" % c0)
+        return out
+
+    def ranked_lists(self, qf: torch.Tensor, q_pids=None, q_camids=None, k: int = 10):
+        """First ``k`` entries of every query's junk-filtered ranked list over the WHOLE (possibly sharded) gallery --
+        what ``visualize_ranked_results`` walks (torchreid/utils/reidtools.py:49,109-145).
+
+        Each rank selects the k best kept items of its gallery slice (``ieee_topk`` with global indices), the
+        per-shard lists are all-gathered and merged (``ieee_topk_merge``): k * world candidates per query instead of
+        a Q x G matrix on one device.  Ties go to the lower global gallery index, as on one GPU.  Pass no labels for an
+        unmasked top-k.  Returns (idx int32 [Q, k'] global gallery indices, -1 padded; dist float32 [Q, k']) on the
+        device, identical on every rank; k' = min(k, total gallery size)."""
+        qf = _as_features(qf)
+        masked = q_pids is not None
+        with torch.cuda.device(self.device):
+            qf = qf.to(self.device, non_blocking=True)
+            Q = qf.shape[0]
+            k_eff = max(1, min(int(k), self.g_total))
+            idx = torch.empty((Q, k_eff), dtype=torch.int32, device=self.device)
+            val = torch.empty((Q, k_eff), dtype=torch.float32, device=self.device)
+            if Q == 0:
+                return idx, val
+            self._ensure_center(qf)
+            if self._host_gallery is not None:
+                if self._copy is None:
+                    self._copy = copy_stream(self.device)
+                self._copy.wait_stream(torch.cuda.current_stream())
+                self._start_gallery_copies(self._copy)
+            qp = _as_device(q_pids, torch.int64, self.device) if masked else None
+            qc = _as_device(q_camids, torch.int64, self.device) if masked else None
+            rows = self._block_rows(Q)
+            self._ensure_block(rows)
+            torch.cuda.current_stream().wait_event(self.labels.ready)
+            for s in range(0, Q, rows):
+                e = min(Q, s + rows)
+                dist = self._distance_block(PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision, self.center))
+                loc_i = idx[s:e] if self.world == 1 else torch.empty((e - s, k_eff), dtype=torch.int32, device=self.device)
+                loc_v = val[s:e] if self.world == 1 else torch.empty((e - s, k_eff), dtype=torch.float32, device=self.device)
+                _lib.call("ieee_topk", dist.data_ptr(), dist.stride(0), e - s, self.G, self.g_offset,
+                          _lib.ptr(qp[s:e] if masked else None), _lib.ptr(qc[s:e] if masked else None),
+                          self.labels.pids.data_ptr() if masked else None, self.labels.camids.data_ptr() if masked else None,
+                          k_eff, loc_i.data_ptr(), loc_v.data_ptr(), _lib.stream())
+                if self.world > 1:
+                    import torch.distributed as dist_
+                    all_i = torch.empty((self.world, e - s, k_eff), dtype=torch.int32, device=self.device)
+                    all_v = torch.empty((self.world, e - s, k_eff), dtype=torch.float32, device=self.device)
+                    dist_.all_gather_into_tensor(all_i, loc_i, group=self.group)
+                    dist_.all_gather_into_tensor(all_v, loc_v, group=self.group)
+                    _lib.call("ieee_topk_merge", all_i.data_ptr(), all_v.data_ptr(), self.world, e - s, k_eff,
+                              idx[s:e].data_ptr(), val[s:e].data_ptr(), _lib.stream())
+        return idx, val
 
     def _rank_block(self, dist, qp, qc, cap, width, ap, first, short, ties, inp):
         Qb = dist.shape[0]
@@ -214,6 +397,7 @@ class RetrievalEvaluator:
         packed and multiplied as soon as it lands, so PCIe time and tensor-core time overlap."""
         _lib.require_cuda()
         dev = device or torch.device("cuda", torch.cuda.current_device())
+        gf_host = _as_features(gf_host)
         with torch.cuda.device(dev):
             self = cls(None, g_pids, g_camids, dist_metric, normalize_feature,
                        precision or ("bf16" if gf_host.dtype == torch.bfloat16 else "f16x3"), max_rank, **kw)
@@ -253,9 +437,7 @@ class RetrievalEvaluator:
                 # sizing pass: the capacity query synchronises once; later calls with the same labels skip it
                 cap = self.labels.list_cap(qp)
                 if memo_key is not None:
-                    if len(_CAP_MEMO) > 64:
-                        _CAP_MEMO.clear()
-                    _CAP_MEMO[memo_key] = (cap, 0)
+                    _memo_put(memo_key, (cap, 0), (self._label_refs, q_pids))
             k_eff = min(self.max_rank, self.g_total)
             prec = _lib.PRECISIONS[self.precision]
             ws, res, res_off, res_host = _fused_buffers(Q, D, prec, cap, k_eff, self.device)
@@ -267,7 +449,7 @@ class RetrievalEvaluator:
             gpk = self.chunks[0][1]
             _lib.call("ieee_retrieve_eval_prepared", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
                       _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
-                      self.G, qp.data_ptr(), qc.data_ptr(), self.labels.camids.data_ptr(), self.max_rank, cap, None,
+                      _lib.ptr(self.center), self.G, qp.data_ptr(), qc.data_ptr(), self.labels.camids.data_ptr(), self.max_rank, cap, None,
                       self._block.data_ptr(), self._block.stride(0), res.data_ptr(), res.data_ptr() + res_off,
                       ap.data_ptr(), first.data_ptr(), ws.data_ptr(), ws.numel(), cur.cuda_stream)
             res_host.copy_(res, non_blocking=True)
@@ -276,7 +458,7 @@ class RetrievalEvaluator:
             cmc_host = out[: 4 * k_eff].view(np.float32).copy()
             summary = _lib.EvalSummary.from_buffer_copy(out[res_off: res_off + 64].tobytes())
         if summary.list_overflow:
-            _CAP_MEMO.pop(memo_key, None)        # stale hint: size the lists again (exact value, so this ends)
+            _memo_drop(memo_key)                 # stale hint: size the lists again (exact value, so this ends)
             return self._evaluate_one_call(qf, q_pids, q_camids, return_distmat, use_cap_memo)
         raise_for_status(summary, self.max_rank)
         info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first,
@@ -291,9 +473,16 @@ class RetrievalEvaluator:
         `qf` may live in (pinned) host memory: it is copied on the copy stream ahead of the gallery chunks."""
         if one_call is None:
             one_call = os.environ.get("IEEE_B200_ONE_CALL", "1") != "0"
+        qf = _as_features(qf)
+        if qf.is_cuda:
+            with torch.cuda.device(self.device):
+                if qf.shape[0] > 0:
+                    self._ensure_center(qf)      # one foreign call: grouping, centre, gallery pack -- the GPU is busy from here on
+                elif self._gallery_dev is not None and not self.chunks:
+                    self._use_center = False     # no query rows to take a centre from (and nothing to compare against)
+                    self._prepare_gallery(None)
         if (one_call and self.world == 1 and qf.is_cuda and self._host_gallery is None and len(self.chunks) == 1
-                and isinstance(self.chunks[0][1], PackedFeatures) and 0 < qf.shape[0] <= self._block_rows(qf.shape[0])
-                and qf.dtype in _lib.DTYPES):
+                and isinstance(self.chunks[0][1], PackedFeatures) and 0 < qf.shape[0] <= self._block_rows(qf.shape[0])):
             return self._evaluate_one_call(qf, q_pids, q_camids, return_distmat, use_cap_memo)
         with torch.cuda.device(self.device):
             TRACE.mark("evaluate: start")
@@ -301,7 +490,8 @@ class RetrievalEvaluator:
             rows = self._block_rows(Q)
             # queries already in HBM: pack the first block before anything else, so the GPU is busy while the host
             # prepares the rest of the step
-            early_pack = PackedFeatures(qf[: min(Q, rows)], self.metric, self.normalize, self.precision) if qf.is_cuda else None
+            early_pack = (PackedFeatures(qf[: min(Q, rows)], self.metric, self.normalize, self.precision, self.center)
+                          if qf.is_cuda else None)
             # small label copies go FIRST: host->device transfers of every stream share one copy engine queue, so a
             # label copy issued after the feature copies would hold the compute stream until they have all landed
             qp = _as_device(q_pids, torch.int64, self.device)
@@ -339,6 +529,10 @@ class RetrievalEvaluator:
                         qf = q_dev
                 if pending_gallery:
                     self._start_gallery_copies(self._copy)
+                if q_event is not None and Q > 0:
+                    # host queries: the centre comes from their device copy, before any chunk is packed
+                    torch.cuda.current_stream().wait_event(q_event)
+                    self._ensure_center(qf)
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             short = torch.empty(Q, dtype=torch.int32, device=self.device)
@@ -348,31 +542,17 @@ class RetrievalEvaluator:
             k_eff = min(self.max_rank, self.g_total)
             res = torch.zeros(32 + 64 + 4 * k_eff, dtype=torch.uint8, device=self.device)
             ties = res[:32].view(torch.int64)
-            if self._block is None or self._block.shape[0] < rows:
-                # row pitch padded to 128 bytes: the contraction's TMA-store epilogue and the rank kernels'
-                # 16-byte loads both want aligned rows (G itself is arbitrary, e.g. 15913)
-                pitch = (self.G + 31) // 32 * 32
-                self._block = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)[:, : self.G]
+            self._ensure_block(rows)
 
             def contraction(s, e):
-                qpk = qf_packed(s, e)
-                out = self._block[: e - s]
-                for i, (c0, gpk) in enumerate(self.chunks):
-                    if isinstance(gpk, tuple):            # (event, host->device staging tensor): pack on arrival
-                        ev, staged = gpk
-                        torch.cuda.current_stream().wait_event(ev)
-                        gpk = PackedFeatures(staged, self.metric, self.normalize, self.precision)
-                        self.chunks[i] = (c0, gpk)        # packed once, reused by later query blocks
-                    packed_distmat(qpk, gpk, out[:, c0: c0 + gpk.rows])
-                    TRACE.mark("  chunk %d contraction" % c0)
-                return out
+                return self._distance_block(qf_packed(s, e))
 
             def qf_packed(s, e):
                 if s == 0 and early_pack is not None:
                     return early_pack
                 if q_event is not None:
                     torch.cuda.current_stream().wait_event(q_event)
-                return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision)
+                return PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision, self.center)
 
             memo_key = None
             if use_cap_memo and self._label_keys[0] is not None and _tensor_key(q_pids) is not None:
@@ -422,14 +602,12 @@ class RetrievalEvaluator:
             cmc_host = out[96:].view(np.float32).copy()
             overflow = overflow or (longest > (width if width > 0 else self.world * cap))   # rows narrower than a merged list
             if memo_key is not None and not overflow:
-                if len(_CAP_MEMO) > 64:
-                    _CAP_MEMO.clear()
-                _CAP_MEMO[memo_key] = (cap, max(longest, 1))
+                _memo_put(memo_key, (cap, max(longest, 1)), (self._label_refs, q_pids))
         if overflow:
             # a list did not fit the (memoised) capacity: forget the hint and run again with the exact value
             if not use_cap_memo:
                 raise RuntimeError("ieee_b200: per-query lists overflowed an exactly sized buffer (cap=%d, longest=%d)" % (cap, longest))
-            _CAP_MEMO.pop(memo_key, None)
+            _memo_drop(memo_key)
             return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False, one_call=one_call)
         TRACE.report()
         raise_for_status(summary, self.max_rank)

@@ -43,9 +43,10 @@ def copy_stream(device) -> torch.cuda.Stream:
 class GalleryLabels:
     """Gallery ids on the device plus their pid-sorted grouping (built once, reused per query block)."""
 
-    def __init__(self, g_pids, g_camids, device, overlap: bool = False):
+    def __init__(self, g_pids, g_camids, device, overlap: bool = False, build: bool = True):
         """overlap=True builds the grouping on the side stream (its few tiny kernels then run beside whatever the
-        caller queues next, e.g. the bandwidth-bound feature packing); consumers order themselves after `ready`."""
+        caller queues next, e.g. the bandwidth-bound feature packing); consumers order themselves after `ready`.
+        build=False only allocates: the caller builds the grouping itself (ieee_gallery_prepare) and sets `ready`."""
         self.pids = _as_device(g_pids, torch.int64, device)
         self.camids = _as_device(g_camids, torch.int64, device)
         self.G = self.pids.numel()
@@ -53,6 +54,9 @@ class GalleryLabels:
         lib = _lib.load()
         self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
         self._scratch = torch.empty(64, dtype=torch.int32, device=device)
+        self.ready = None
+        if not build:
+            return
         with torch.cuda.device(device):
             cur = torch.cuda.current_stream()
             if overlap:

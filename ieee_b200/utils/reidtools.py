@@ -27,14 +27,21 @@ GRID_SPACING, QUERY_EXTRA_SPACING, BW = 10, 90, 5
 BLACK, GREEN, RED = (0, 0, 0), (0, 255, 0), (0, 0, 255)      # BGR: query frame, true match, false match
 
 
-def ranked_lists(distmat, dataset, topk=10):
+def ranked_lists(distmat, dataset, topk=10, ranked=None):
     """(idx int32 [Q, topk'], matched bool [Q, topk']) -- the gallery entries reidtools.py:109-145 would show for every
-    query, in order (topk' = min(topk, G)); idx is -1 where a query keeps fewer gallery items than that."""
+    query, in order (topk' = min(topk, G)); idx is -1 where a query keeps fewer gallery items than that.
+    ranked: lists computed elsewhere -- RetrievalEvaluator.ranked_lists(...) over a gallery sharded across GPUs, where no
+    rank ever holds the Q x G matrix -- as idx or (idx, dist) with GLOBAL gallery indices; distmat is then unused."""
     query, gallery = dataset
     q_pid, q_cam = (np.asarray([e[i] for e in query], dtype=np.int64) for i in (1, 2))
     g_pid, g_cam = (np.asarray([e[i] for e in gallery], dtype=np.int64) for i in (1, 2))
     k = max(1, min(int(topk), len(gallery)))
-    idx = topk_ranked_list(distmat, q_pid, g_pid, q_cam, g_cam, k=k)[0].cpu().numpy()
+    if ranked is not None:
+        idx = ranked[0] if isinstance(ranked, (tuple, list)) else ranked
+        idx = (idx.cpu().numpy() if hasattr(idx, "cpu") else np.asarray(idx))[:, :k].astype(np.int32)
+        assert idx.shape[0] == len(query), "ranked lists must have one row per query"
+    else:
+        idx = topk_ranked_list(distmat, q_pid, g_pid, q_cam, g_cam, k=k)[0].cpu().numpy()
     found = idx >= 0
     matched = np.zeros(idx.shape, dtype=bool)
     matched[found] = g_pid[idx[found]] == np.broadcast_to(q_pid[:, None], idx.shape)[found]
@@ -78,10 +85,11 @@ def _export(src, folder, label):
         shutil.copy(src, osp.join(folder, label.split('_TRUE')[0].split('_FALSE')[0] + '_name_' + osp.basename(src)))
 
 
-def visualize_ranked_results(distmat, dataset, data_type, width=128, height=256, save_dir='', topk=10):
+def visualize_ranked_results(distmat, dataset, data_type, width=128, height=256, save_dir='', topk=10, ranked=None):
     """Visualizes ranked results (image-reid: one grid figure per query; video-reid: one folder per query with the
-    ranked tracklets).  Arguments as torchreid/utils/reidtools.py:18-39."""
-    num_q, num_g = distmat.shape
+    ranked tracklets).  Arguments as torchreid/utils/reidtools.py:18-39, plus ``ranked``: precomputed lists (see
+    ``ranked_lists``), in which case ``distmat`` may be None."""
+    num_q, num_g = (len(dataset[0]), len(dataset[1])) if distmat is None else distmat.shape
     if save_dir:
         os.makedirs(save_dir, exist_ok=True)
     print('# query: {}\n# gallery {}'.format(num_q, num_g))
@@ -89,7 +97,7 @@ def visualize_ranked_results(distmat, dataset, data_type, width=128, height=256,
     query, gallery = dataset
     assert num_q == len(query)
     assert num_g == len(gallery)
-    idx, matched = ranked_lists(distmat, dataset, topk)
+    idx, matched = ranked_lists(distmat, dataset, topk, ranked)
     as_image = data_type == 'image'
     if as_image:
         import cv2

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define IEEE_B200_ABI_VERSION 2
+#define IEEE_B200_ABI_VERSION 3
 
 typedef void* ieee_stream_t; /* cudaStream_t */
 
@@ -69,13 +69,22 @@ int ieee_device_info(int* sm_count, int* compute_capability);
 int ieee_set_cta_group(int cta_group);
 /* Accumulation chunking of the tensor-core contraction: the tcgen05 fp32 accumulator truncates, so
  * every `k_slices` 64-wide K-slices the partial sums are moved to registers and added there with round-to-nearest.
- * 0 = accumulate the whole K in TMEM (fastest, ~1e-5 relative bias on the dot product); default 4 (F16X3 mode;
+ * 0 = accumulate the whole K in TMEM (fastest, ~1e-5 relative bias on the dot product); default 6 (F16X3 mode;
  * the 1-pass BF16 mode always accumulates the whole K in TMEM).
  * Returns the previous value. */
 int ieee_set_accum_chunk(int k_slices);
+/* Tile raster of the contraction: m tiles (256 query rows each with cta_group 2) per panel; inside a panel m runs
+ * fastest, so one panel's query rows stay L2-resident while it sweeps every gallery tile.  0 (default) sizes the
+ * panel for ~40 MB of query operand.  Negative: query only.  Returns the previous value. */
+int ieee_set_raster_panel(int m_tiles);
+/* Whether the one-call entry points (ieee_distmat, ieee_retrieve_eval) centre euclidean operands on the query
+ * set's mean (see ieee_feature_center).  Default 1; 0 reproduces the uncentred arithmetic of ABI 2 (accuracy
+ * studies).  Negative: query only.  Returns the previous value. */
+int ieee_set_centering(int on);
 /* Diagnostics for kernel tuning (results are WRONG when non-zero): bit 0 = tensor-core epilogue skips its global
  * stores, bit 1 = epilogue also skips the TMEM reads, bit 2 = no TMA store, bit 3 = chunk BF16 mode too, bit 4 = count
- * stage always uses the CTA-per-query kernel with shared atomics (results stay correct).  Returns the previous value. */
+ * stage always uses the CTA-per-query kernel with shared atomics (results stay correct), bit 5 = no near-duplicate
+ * fix-up pass (results stay within the accumulator's floor).  Returns the previous value. */
 int ieee_set_debug_flags(int flags);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
 int64_t ieee_launch_count(void);
@@ -90,12 +99,31 @@ int64_t ieee_launch_count(void);
  * power-of-two row scale).  Pack a gallery once, reuse it for every query block.
  * ---------------------------------------------------------------------------------------------- */
 size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision);
+/* center: NULL, or float32[D] (16-byte aligned) subtracted from every (normalised) row before it is split; euclidean
+ * only.  |q - g|^2 does not change when the same vector is subtracted from q and g, but the fp32 evaluation of
+ * |q|^2 + |g|^2 - 2 q.g loses |q|^2 + |g|^2 times a few ulps to cancellation (distance.py:59-64 does too): with the
+ * common component of the post-ReLU features removed, that scale shrinks to the spread of the data and the tensor
+ * core's truncating accumulator sees mixed-sign products.  Both operands of a contraction MUST be packed with the
+ * same centre. */
 int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,
-                       int precision, void* packed, ieee_stream_t stream);
+                       int precision, const float* center, void* packed, ieee_stream_t stream);
+/* Centre for ieee_pack_features: column mean over up to max_rows (0: 512) evenly strided rows of x, scaled to unit
+ * length when `normalize` is set (the rows will be).  Deterministic (fixed summation order).  center: float32[D];
+ * workspace: ieee_feature_center_workspace_bytes(D). */
+size_t ieee_feature_center_workspace_bytes(int64_t D);
+int ieee_feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
+                        float* center, void* workspace, ieee_stream_t stream);
+/* fixup_workspace: NULL, or ieee_distmat_fixup_bytes(Q) bytes (8-byte aligned).  With it (euclidean, F16X3) every
+ * output below 2^-6 of its scale |q|^2 + |g|^2 -- near-duplicate pairs, where the expansion |q|^2 + |g|^2 - 2 q.g only
+ * keeps the ABSOLUTE accuracy of its terms -- is listed by the contraction and recomputed as sum_k (q_k - g_k)^2 by
+ * a second small kernel: all distances then sit within 1e-4 relative of the exact value.  Word 0 of the workspace
+ * holds the number of pairs found (up to 2 Q + 4096 are recomputed). */
+size_t ieee_distmat_fixup_bytes(int64_t Q);
 int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
-                        int precision, float* out, int64_t ldo, ieee_stream_t stream);
+                        int precision, float* out, int64_t ldo, void* fixup_workspace, ieee_stream_t stream);
 size_t ieee_distmat_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision);
-/* One call: pack both sides into the workspace, then the contraction.  out[Q, G] float32, leading dim ldo. */
+/* One call: [centre on q's rows ->] pack both sides into the workspace, then the contraction.  out[Q, G] float32,
+ * leading dim ldo. */
 int ieee_distmat(const void* q, const void* g, int dtype, int64_t ldq, int64_t ldg, int64_t Q, int64_t G, int64_t D,
                  int metric, int normalize, int precision, float* out, int64_t ldo, void* workspace,
                  size_t workspace_bytes, ieee_stream_t stream);
@@ -204,12 +232,23 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
                          int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
                          ieee_stream_t stream);
 
+/* Gallery side of an evaluation in ONE call: identity grouping (on an internal side stream, joined before return),
+ * [centre from the rows of center_src -- normally the query features --] and feature packing.
+ * center_src != NULL: its column mean is written to center (float32[D]) and used;  center_src == NULL: center is an
+ * INPUT (or NULL: uncentred).  g_pids / group may be NULL to skip the grouping.  workspace:
+ * ieee_gallery_prepare_workspace_bytes(D) (only needed with center_src). */
+size_t ieee_gallery_prepare_workspace_bytes(int64_t D);
+int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int64_t D, int metric, int normalize,
+                         int precision, const int64_t* g_pids, const void* center_src, int64_t ld_src, int64_t rows_src,
+                         float* center, void* g_packed, void* group, void* workspace, ieee_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Retrieval + evaluation in ONE call: the tail of Engine._evaluate (engine.py:391-417) --
  * [normalise] -> distance matrix -> Market-1501 CMC / mAP -- enqueued back to back on `stream` from C, so a
  * binding pays one foreign call per evaluation instead of one per kernel.
  *
- * ieee_retrieve_eval           raw query AND gallery features + labels in, (cmc, summary) out.
+ * ieee_retrieve_eval           raw query AND gallery features + labels in, (cmc, summary) out; euclidean operands
+ *                              are centred on the query set (ieee_set_centering).
  * ieee_retrieve_eval_prepared  the gallery side was prepared once (ieee_pack_features + ieee_gallery_group)
  *                              and is reused for every query set.
  * cap > 0  : list-capacity HINT (e.g. the value a previous call reported); fully asynchronous.  If a query needs
@@ -229,7 +268,8 @@ int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg,
                        size_t workspace_bytes, ieee_stream_t stream);
 size_t ieee_retrieve_prepared_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap);
 int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
-                                int precision, const void* g_packed, const void* group, int64_t G,
+                                int precision, const void* g_packed, const void* group,
+                                const float* center /* the centre g_packed was packed with, or NULL */, int64_t G,
                                 const int64_t* q_pids, const int64_t* q_camids, const int64_t* g_camids,
                                 int32_t max_rank, int32_t cap, int32_t* cap_host_out, float* distmat, int64_t ld,
                                 float* cmc, ieee_eval_summary* summary, double* per_query_ap,

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = _lib.load()
-    assert lib.ieee_abi_version() == 2
+    assert lib.ieee_abi_version() == 3
     assert ctypes.sizeof(_lib.EvalSummary) == 64
 
 

@@ -83,6 +83,75 @@ def test_topk_merge_across_shards():
     assert np.array_equal(idx.cpu().numpy(), idx_o) and np.array_equal(val.cpu().numpy(), val_o)
 
 
+def _tied_set():
+    """Gallery with rows duplicated ACROSS the two shards: bit-equal distances on different ranks, so the merged order
+    depends on the global-index tie rule."""
+    s = make_retrieval_set(300, 2001, 30, 4, dim=256, sigma=2.5, seed=23, distractor_frac=0.1)
+    gf = s.gf.clone()
+    g_pids, g_camids = s.g_pids.copy(), s.g_camids.copy()
+    src = np.arange(0, 400, 2)
+    dst = 2001 - 1 - src                                # second shard (rows >= 1001)
+    gf[dst] = gf[src]
+    g_pids[dst], g_camids[dst] = g_pids[src], (g_camids[src] + 1) % 4
+    return s, gf, g_pids, g_camids
+
+
+def _ranked_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    s, gf, g_pids, g_camids = _tied_set()
+    G = gf.shape[0]
+    g0, g1 = shard_bounds(G, world, rank)
+    ev = RetrievalEvaluator(gf[g0:g1].cuda(), g_pids[g0:g1], g_camids[g0:g1], group=dist.group.WORLD, g_offset=g0, g_total=G)
+    cmc, mAP, info = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True)
+    idx, val = ev.ranked_lists(s.qf.cuda(), s.q_pids, s.q_camids, k=25)
+    idx_u, _ = ev.ranked_lists(s.qf.cuda(), k=7)        # unmasked
+    gathered = [torch.empty((300, shard_bounds(G, world, r)[1] - shard_bounds(G, world, r)[0]), device="cuda") for r in range(world)]
+    dist.all_gather(gathered, info["distmat"].contiguous())
+    if rank == 0:
+        out["idx"], out["val"], out["idx_u"] = idx.cpu().numpy(), val.cpu().numpy(), idx_u.cpu().numpy()
+        out["d"] = torch.cat(gathered, 1).cpu().numpy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_ranked_lists():
+    """north_star: local top-k per gallery slice, all-gather over NVLink, merge -- bit-exact incl. ties across shards."""
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_ranked_worker, args=(2, port, out), nprocs=2, join=True)
+    s, gf, g_pids, g_camids = _tied_set()
+    d = out["d"]
+    assert (d[:, 0] == d[:, 2000]).all()                                   # the duplicates really tie across the shards
+    idx_o, val_o = R.topk_kept(d, s.q_pids, g_pids, s.q_camids, g_camids, 25)
+    assert np.array_equal(out["idx"], idx_o) and np.array_equal(out["val"], val_o)
+    none = np.full(300, -1)
+    idx_uo, _ = R.topk_kept(d, none, g_pids, none - 1, g_camids, 7)
+    assert np.array_equal(out["idx_u"], idx_uo)
+
+
+def test_ranked_lists_on_one_gpu(tmp_path):
+    s, gf, g_pids, g_camids = _tied_set()
+    ev = RetrievalEvaluator(gf.cuda(), g_pids, g_camids, block_bytes=128 * 2001 * 4)      # several query blocks
+    _, _, info = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True)
+    d = info["distmat"].cpu().numpy()
+    idx, val = ev.ranked_lists(s.qf, s.q_pids, s.q_camids, k=25)                           # host queries are copied
+    idx_o, val_o = R.topk_kept(d, s.q_pids, g_pids, s.q_camids, g_camids, 25)
+    assert np.array_equal(idx.cpu().numpy(), idx_o) and np.array_equal(val.cpu().numpy(), val_o)
+    # the consumer takes the lists instead of a Q x G matrix (reidtools.py:49,109-145)
+    from ieee_b200.utils.reidtools import ranked_lists
+    dataset = ([("q%d.jpg" % i, int(p), int(c)) for i, (p, c) in enumerate(zip(s.q_pids, s.q_camids))],
+               [("g%d.jpg" % i, int(p), int(c)) for i, (p, c) in enumerate(zip(g_pids, g_camids))])
+    a = ranked_lists(d, dataset, topk=10)
+    b = ranked_lists(None, dataset, topk=10, ranked=(idx, val))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def _nccl_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)

@@ -104,3 +104,41 @@ def test_sharded_protocol_equals_single_process_oracle(world):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), distmat, q_pids, g_pids, q_cams, g_cams, 20, out), nprocs=world, join=True)
     assert np.array_equal(out["cmc"], cmc_o) and abs(out["mAP"] - map_o) < 1e-12 and out["nv"] == Q - 2
+
+
+def _topk_worker(rank, world, port, distmat, q_pids, g_pids, q_cams, g_cams, k, out):
+    """Ranked lists over a sharded gallery (RetrievalEvaluator.ranked_lists): local junk-masked top-k with global
+    indices -> all_gather -> merge by (distance, global index)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Q, G = distmat.shape
+    g0, g1 = shard_bounds(G, world, rank)
+    idx_l, val_l = R.topk_kept(distmat[:, g0:g1], q_pids, g_pids[g0:g1], q_cams, g_cams[g0:g1], k)
+    idx_l = np.where(idx_l >= 0, idx_l + g0, -1)                          # global indices (ieee_topk's g_offset)
+    bi = [torch.empty(Q, k, dtype=torch.int64) for _ in range(world)]
+    bv = [torch.empty(Q, k, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(bi, torch.from_numpy(idx_l))
+    dist.all_gather(bv, torch.from_numpy(val_l.astype(np.float64)))
+    ci, cv = torch.cat(bi, 1).numpy(), torch.cat(bv, 1).numpy()
+    idx = np.full((Q, k), -1, dtype=np.int64)
+    for q in range(Q):
+        live = ci[q] >= 0
+        order = np.lexsort((ci[q][live], cv[q][live]))[:k]                # ieee_topk_merge: k smallest (d, index)
+        idx[q, : order.size] = ci[q][live][order]
+    if rank == 0:
+        out["idx"] = idx
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_topk_merge_equals_single_process_oracle(world):
+    rng = np.random.RandomState(9)
+    Q, G, k = 30, 211, 12
+    distmat = rng.randint(0, 40, size=(Q, G)).astype(np.float32)       # heavy ties across shard boundaries
+    q_pids, g_pids = rng.randint(0, 10, Q), rng.randint(0, 10, G)
+    q_cams, g_cams = rng.randint(0, 3, Q), rng.randint(0, 3, G)
+    idx_o, _ = R.topk_kept(distmat, q_pids, g_pids, q_cams, g_cams, k)
+    out = mp.Manager().dict()
+    mp.spawn(_topk_worker, args=(world, _free_port(), distmat, q_pids, g_pids, q_cams, g_cams, k, out), nprocs=world, join=True)
+    assert np.array_equal(out["idx"], idx_o)
