@@ -69,6 +69,31 @@ SIGNATURES = {
     "ieee_rerank": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
 }
 
+MAX_PEERS = 16
+
+
+class PeerExchange(C.Structure):
+    _fields_ = [("shards", i32), ("my_shard", i32), ("epoch", C.c_uint64), ("base", vp * MAX_PEERS),
+                ("Qb_max", i64), ("Qb", i64), ("Qtot", i64), ("q_base", i64), ("cap", i32), ("W", i32)]
+
+
+_PEER = C.POINTER(PeerExchange)
+SIGNATURES.update({
+    "ieee_peer_exchange_bytes": (sz, [i64, i64, i32, i32, i32]),
+    "ieee_peer_alloc": (C.c_int, [sz, C.POINTER(vp), vp]),
+    "ieee_peer_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "ieee_peer_close": (C.c_int, [vp]),
+    "ieee_peer_free": (C.c_int, [vp]),
+    "ieee_rank_gather_peer": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, _PEER, vp]),
+    "ieee_rank_count_peer": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, _PEER, vp]),
+    "ieee_rank_owner_metrics_peer": (C.c_int, [i64, i32, vp, _PEER, vp]),
+    "ieee_rank_reduce_peer": (C.c_int, [i32, vp, vp, vp, _PEER, vp]),
+    "ieee_peer_result_offset": (sz, [C.c_int, i64, i64, i32, i32, i32]),
+    "ieee_retrieve_prepared_peer_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
+    "ieee_retrieve_eval_prepared_peer": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, i64, i64,
+                                                   vp, vp, vp, i32, vp, i64, vp, vp, vp, _PEER, vp, sz, vp]),
+})
+
 _lib = None
 
 

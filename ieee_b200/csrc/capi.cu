@@ -51,18 +51,20 @@ int gallery_group(const int64_t* g_pids, int64_t G, void* blob, cudaStream_t str
 int rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q, int32_t* cap_dev, cudaStream_t stream);
 int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
                 const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel, int32_t* n_rel,
-                uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream);
+                uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream, const PeerView* peers = nullptr);
 size_t rank_count_smem(int shards, int cap);
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
-               int32_t* counts, unsigned long long* ties, cudaStream_t stream);
+               int32_t* counts, unsigned long long* ties, cudaStream_t stream, const PeerView* peers = nullptr);
+int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
+                       cudaStream_t stream);
 size_t rank_finalize_workspace_bytes(int64_t Q);
 int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                        int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, double* inp,
                        cudaStream_t stream);
 int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
                 const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, const double* inp,
-                const int32_t* overflow, cudaStream_t stream);
+                const int32_t* overflow, cudaStream_t stream, const PeerView* peers = nullptr, long long* stats_out = nullptr);
 int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                   double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream,
@@ -547,6 +549,181 @@ int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq
   if (rc) return rc;
   return rerank(q_g, ld_qg, q_q, ld_qq, g_g, ld_gg, Q, G, k1, k2, lambda_value, out, ldo, workspace, workspace_bytes,
                 (cudaStream_t)stream);
+}
+
+// ---- peer exchange (gallery sharded over the GPUs of one box) ---------------------------------------------------
+// regions are sized for the largest query block (Qb_max); a block of Qb <= Qb_max rows uses a dense prefix of each
+static size_t peer_layout(int64_t Qb_max, int64_t Qb, int64_t Qtot, int32_t cap, int32_t W, int32_t shards, PeerView* v) {
+  size_t o = kPeerHeaderBytes;
+  const int64_t Qown_max = (Qb_max + shards - 1) / shards, Qown = (Qb + shards - 1) / shards;
+  auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
+  const size_t off_rel = take(size_t(shards) * Qb_max * (cap + 1) * 8);
+  const size_t off_cnt = take(size_t(shards) * Qown_max * (W + 2) * 4);
+  const size_t off_ap = take(size_t(Qtot) * 8), off_inp = take(size_t(Qtot) * 8);
+  const size_t off_first = take(size_t(Qtot) * 4), off_short = take(size_t(Qtot) * 4);
+  if (v) {
+    v->off_rel = off_rel; v->off_cnt = off_cnt; v->off_ap = off_ap; v->off_inp = off_inp;
+    v->off_first = off_first; v->off_short = off_short;
+    v->Qb = Qb; v->Qown = (int)Qown; v->cap = cap; v->W = W;
+  }
+  return o;
+}
+
+size_t ieee_peer_exchange_bytes(int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards) {
+  if (Qb_max <= 0 || Qtot < Qb_max || cap < 1 || W < 1 || shards < 1 || shards > kMaxPeers) return 0;
+  return peer_layout(Qb_max, Qb_max, Qtot, cap, W, shards, nullptr);
+}
+
+int ieee_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(ptr && ipc_handle_out && bytes >= kPeerHeaderBytes, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  IEEE_CUDA_CHECK(cudaMalloc(ptr, bytes));
+  IEEE_CUDA_CHECK(cudaMemset(*ptr, 0, bytes));
+  IEEE_CUDA_CHECK(cudaDeviceSynchronize());
+  IEEE_CUDA_CHECK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(ipc_handle_out), *ptr));
+  return IEEE_OK;
+}
+
+int ieee_peer_open(const void* ipc_handle, void** ptr) {
+  int rc = check_device();
+  if (rc) return rc;
+  IEEE_REQUIRE(ipc_handle && ptr, "peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  IEEE_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return IEEE_OK;
+}
+
+int ieee_peer_close(void* ptr) {
+  if (ptr) IEEE_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+  return IEEE_OK;
+}
+
+int ieee_peer_free(void* ptr) {
+  if (ptr) IEEE_CUDA_CHECK(cudaFree(ptr));
+  return IEEE_OK;
+}
+
+static int peer_view(const ieee_peer_exchange* ex, PeerView* v) {
+  IEEE_REQUIRE(ex != nullptr, "peer exchange: null descriptor");
+  IEEE_REQUIRE(ex->shards >= 1 && ex->shards <= kMaxPeers && ex->my_shard >= 0 && ex->my_shard < ex->shards,
+               "peer exchange: bad shard %d of %d", ex->my_shard, ex->shards);
+  IEEE_REQUIRE(ex->Qb > 0 && ex->Qb <= ex->Qb_max && ex->q_base >= 0 && ex->q_base + ex->Qb <= ex->Qtot && ex->cap >= 1 &&
+                   ex->W >= 1 && ex->epoch > 0,
+               "peer exchange: bad block (Qb=%lld q_base=%lld Qtot=%lld cap=%d W=%d)", (long long)ex->Qb,
+               (long long)ex->q_base, (long long)ex->Qtot, ex->cap, ex->W);
+  *v = no_peers();
+  v->shards = ex->shards;
+  v->my = ex->my_shard;
+  v->epoch = ex->epoch;
+  for (int s = 0; s < ex->shards; ++s) {
+    IEEE_REQUIRE(ex->base[s] != nullptr, "peer exchange: buffer of shard %d is not mapped", s);
+    v->base[s] = static_cast<uint8_t*>(ex->base[s]);
+  }
+  peer_layout(ex->Qb_max, ex->Qb, ex->Qtot, ex->cap, ex->W, ex->shards, v);
+  v->q_base = ex->q_base;
+  return IEEE_OK;
+}
+
+int ieee_rank_gather_peer(const float* distmat, int64_t ld, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                          const int64_t* g_camids, const void* group, int64_t g_offset, int32_t* n_rel, uint64_t* junk,
+                          int32_t* n_junk, unsigned long long* stats, const ieee_peer_exchange* ex, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PeerView v;
+  if ((rc = peer_view(ex, &v))) return rc;
+  IEEE_REQUIRE(stats != nullptr, "rank_gather_peer: null pointer");
+  return rank_gather(distmat, ld, v.Qb, G, q_pids, q_camids, g_camids, group, g_offset, v.cap, nullptr, n_rel, junk, n_junk,
+                     reinterpret_cast<int32_t*>(stats), (cudaStream_t)stream, &v);
+}
+
+int ieee_rank_count_peer(const float* distmat, int64_t ld, int64_t G, int64_t g_offset, const int32_t* n_rel,
+                         const uint64_t* junk, const int32_t* n_junk, unsigned long long* stats,
+                         const ieee_peer_exchange* ex, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PeerView v;
+  if ((rc = peer_view(ex, &v))) return rc;
+  IEEE_REQUIRE(stats != nullptr, "rank_count_peer: null pointer");
+  const uint64_t* rel_all = reinterpret_cast<const uint64_t*>(v.base[v.my] + v.off_rel);
+  return rank_count(distmat, ld, v.Qb, G, g_offset, v.shards, v.cap, v.W, rel_all, n_rel, junk, n_junk, nullptr, stats + 1,
+                    (cudaStream_t)stream, &v);
+}
+
+int ieee_rank_owner_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats,
+                                 const ieee_peer_exchange* ex, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PeerView v;
+  if ((rc = peer_view(ex, &v))) return rc;
+  return rank_owner_metrics(&v, G_total, max_rank, stats, (cudaStream_t)stream);
+}
+
+int ieee_rank_reduce_peer(int32_t max_rank, float* cmc, ieee_eval_summary* summary, int64_t* stats_out,
+                          const ieee_peer_exchange* ex, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PeerView v;
+  if ((rc = peer_view(ex, &v))) return rc;
+  uint8_t* mine = v.base[v.my];
+  return rank_reduce(reinterpret_cast<const double*>(mine + v.off_ap), reinterpret_cast<const int32_t*>(mine + v.off_first),
+                     reinterpret_cast<const int32_t*>(mine + v.off_short), ex->Qtot, max_rank, nullptr, cmc, summary,
+                     reinterpret_cast<const double*>(mine + v.off_inp), nullptr, (cudaStream_t)stream, &v,
+                     reinterpret_cast<long long*>(stats_out));
+}
+
+size_t ieee_retrieve_prepared_peer_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap) {
+  if (Q <= 0 || D <= 0 || cap < 1) return 0;
+  return align256(ieee_packed_bytes(Q, D, precision)) + distmat_fixup_bytes(Q) + align256(size_t(Q) * cap * 8) +
+         2 * align256(size_t(Q) * 4) + 256 + 256;
+}
+
+int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
+                                     int precision, const void* g_packed, const void* group, const float* center, int64_t G,
+                                     int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
+                                     const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
+                                     ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
+                                     void* workspace, size_t workspace_bytes, ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(qf && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace && ex,
+               "retrieve (peer): null pointer");
+  IEEE_REQUIRE(Q > 0 && G > 0 && D > 0 && ld >= G && max_rank >= 1 && G_total >= G && g_offset >= 0,
+               "retrieve (peer): bad shape Q=%lld G=%lld D=%lld ld=%lld", (long long)Q, (long long)G, (long long)D, (long long)ld);
+  IEEE_REQUIRE(ex->Qb == Q && ex->Qtot == Q && ex->q_base == 0, "retrieve (peer): the exchange must describe one block of Q rows");
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve (peer): workspace must be 256-byte aligned");
+  const int32_t cap = ex->cap;
+  Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
+  void* q_packed = a.take(ieee_packed_bytes(Q, D, precision));
+  void* fix = a.take(distmat_fixup_bytes(Q));
+  uint64_t* junk = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
+  int32_t* n_rel = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  int32_t* n_junk = static_cast<int32_t*>(a.take(size_t(Q) * 4));
+  unsigned long long* stats = static_cast<unsigned long long*>(a.take(256));   // this rank's own statistics
+  if (!q_packed || !fix || !junk || !n_rel || !n_junk || !stats) {
+    set_error("retrieve (peer): workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
+              ieee_retrieve_prepared_peer_workspace_bytes(Q, D, precision, cap), cap);
+    return IEEE_ERR_WORKSPACE;
+  }
+  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
+  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
+  IEEE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 256, stream));
+  if ((rc = ieee_rank_gather_peer(distmat, ld, G, q_pids, q_camids, g_camids, group, g_offset, n_rel, junk, n_junk, stats, ex,
+                                  stream_)))
+    return rc;
+  if ((rc = ieee_rank_count_peer(distmat, ld, G, g_offset, n_rel, junk, n_junk, stats, ex, stream_))) return rc;
+  if ((rc = ieee_rank_owner_metrics_peer(G_total, max_rank, stats, ex, stream_))) return rc;
+  return ieee_rank_reduce_peer(max_rank > G_total ? (int32_t)G_total : max_rank, cmc, summary, stats_out, ex, stream_);
+}
+
+size_t ieee_peer_result_offset(int which, int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards) {
+  PeerView v = no_peers();
+  if (ieee_peer_exchange_bytes(Qb_max, Qtot, cap, W, shards) == 0) return 0;
+  peer_layout(Qb_max, Qb_max, Qtot, cap, W, shards, &v);
+  return which == 0 ? v.off_ap : (which == 1 ? v.off_first : (which == 2 ? v.off_inp : v.off_short));
 }
 
 }  // extern "C"

@@ -109,8 +109,74 @@ inline PackedLayout packed_layout(int64_t rows, int64_t D, int precision) {
   return L;
 }
 
+// ---- exchange between the ranks of a sharded gallery over NVLink peer memory ----------------------------------
+// Every rank owns one exchange buffer (ieee_peer_alloc) that all ranks of the gallery group map (cudaIpc): the rank
+// kernels STORE their lists / partial counts / per-query results straight into the peers' buffers and hand over with
+// flag words, instead of an all-gather + all-reduce per query block.  Header (first 1 KB of a buffer):
+//   [0, 128)    flag A[s]: epoch of the last block whose relevant lists from shard s have landed here
+//   [128, 256)  flag B[s]: ... whose partial counts from shard s have landed here
+//   [256, 384)  flag C[s]: ... whose per-query results from owner s have landed here
+//   [384, 408)  sent[3]:   (local) epoch this rank has already signalled per phase
+//   [512, ...)  stats[s][4]: shard s' {gather overflow, tie pairs, longest merged list, -}
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerHeaderBytes = 1024;
+struct PeerView {
+  int shards, my;                  // shards == 0: no peer exchange (single GPU / NCCL path)
+  unsigned long long epoch;        // one per query block, increasing
+  uint8_t* base[kMaxPeers];        // every rank's buffer as mapped into this process; base[my] is this rank's own
+  unsigned long long off_rel;      // uint64 [shards][Qb][cap + 1]   relevant lists (+ length), slot s written by shard s
+  unsigned long long off_cnt;      // int32  [shards][Qown][W + 2]   partial counts of the queries this rank owns
+  unsigned long long off_ap, off_inp, off_first, off_short;   // per-query results [Qtot]: f64, f64, i32, i32
+  long long Qb, q_base;            // rows of this query block; index of its first query in the result arrays
+  int Qown, cap, W;                // queries per owner = ceil(Qb / shards); list capacity; count row width
+};
+inline PeerView no_peers() { PeerView v; memset(&v, 0, sizeof(v)); return v; }
+
 // ---- raw PTX: mbarrier / TMA / tcgen05 ----------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Called by every thread of every CTA at the top of the kernel that CONSUMES phase `phase` (0 lists, 1 partial counts,
+// 2 per-query results).  The producing kernel is the previous one on this stream, so all of this rank's stores --
+// including the ones into peer buffers -- are complete when any CTA of this kernel runs: the first CTA to get here
+// publishes them (fence, then one flag store per peer), then everybody waits until every peer has done the same.
+// `stats_src` (4 words, may be null) is copied into this rank's stats slot of every peer before the flags.
+// The wait is bounded like mbar_wait: a peer that never arrives traps instead of hanging the box.
+__device__ __forceinline__ void peer_signal_and_wait(const PeerView& pv, int phase, const unsigned long long* stats_src = nullptr) {
+  if (threadIdx.x == 0) {
+    unsigned long long* sent = reinterpret_cast<unsigned long long*>(pv.base[pv.my] + 384) + phase;
+    if (atomicMax(sent, pv.epoch) < pv.epoch) {
+      if (stats_src != nullptr) {
+        for (int s = 0; s < pv.shards; ++s) {
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.base[s] + 512) + 4 * pv.my;
+          for (int i = 0; i < 4; ++i) dst[i] = stats_src[i];
+        }
+      }
+      __threadfence_system();
+      for (int s = 0; s < pv.shards; ++s)
+        st_release_sys(reinterpret_cast<unsigned long long*>(pv.base[s] + 128 * phase) + pv.my, pv.epoch);
+    }
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.base[pv.my] + 128 * phase);
+    const long long t0 = clock64();
+    for (int s = 0; s < pv.shards; ++s) {
+      while (ld_acquire_sys(mine + s) < pv.epoch) {
+        if (clock64() - t0 > 8000000000ll) {
+          printf("ieee_b200: rank %d waited in vain for shard %d (phase %d, epoch %llu)\n", pv.my, s, phase, pv.epoch);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

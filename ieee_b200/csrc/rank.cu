@@ -169,10 +169,17 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
                                                            const int32_t* __restrict__ members, int64_t T, int64_t g_offset,
                                                            int32_t cap, uint64_t* __restrict__ rel, int32_t* __restrict__ n_rel,
                                                            uint64_t* __restrict__ junk, int32_t* __restrict__ n_junk,
-                                                           int32_t* __restrict__ overflow) {
+                                                           int32_t* __restrict__ overflow, const PeerView pv) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
+  // peer exchange: this shard's list goes straight into slot `my` of EVERY rank's list table (posted NVLink stores;
+  // the count kernel hands over with the phase-A flags), instead of a local list + all-gather
+  auto put_rel = [&](int slot, uint64_t v) {
+    if (pv.shards == 0) { rel[q * (cap + 1) + slot] = v; return; }
+    for (int p = 0; p < pv.shards; ++p)
+      (reinterpret_cast<uint64_t*>(pv.base[p] + pv.off_rel) + ((int64_t)pv.my * Q + q) * (cap + 1))[slot] = v;
+  };
   const int64_t cam = q_camids[q];
   int lo = 0, n = 0;
   if (lane == 0) {
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
     }
     const unsigned mr = __ballot_sync(0xffffffffu, is_rel), mj = __ballot_sync(0xffffffffu, is_junk);
     const unsigned below = (1u << lane) - 1;
-    if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) rel[q * (cap + 1) + s] = key; }
+    if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) put_rel(s, key); }
     if (is_junk) { const int s = nj + __popc(mj & below); if (s < cap) junk[q * cap + s] = key; }
     nr += __popc(mr);
     nj += __popc(mj);
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
   if (lane == 0) {
     if (nr > cap || nj > cap) { atomicMax(overflow, max(nr, nj)); nr = min(nr, cap); nj = min(nj, cap); }
     n_rel[q] = nr;
-    rel[q * (cap + 1) + cap] = (uint64_t)nr;      // the list carries its own length: one all-gather moves both
+    put_rel(cap, (uint64_t)nr);                   // the list carries its own length: one exchange moves both
     n_junk[q] = nj;
   }
 }
@@ -505,8 +512,9 @@ __global__ void __launch_bounds__(32 * kWarpQ)
 rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
                        int out_cap, int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                        const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
-                       unsigned long long* __restrict__ ties_out) {
+                       unsigned long long* __restrict__ ties_out, const PeerView pv) {
   static_assert(WPQ == 1 || WPQ == kWarpQ, "one warp or the whole CTA per query");
+  if (pv.shards) peer_signal_and_wait(pv, 0);      // every shard's relevant lists have landed in rel_all
   constexpr bool kTeam = WPQ > 1;
   extern __shared__ __align__(16) uint8_t ws_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -522,6 +530,10 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   if (q >= Q) return;
   const int stride = out_cap + 2;
   int32_t* out = counts + q * stride;
+  if (pv.shards) {   // partial counts go to the rank that owns query q (posted stores into its table, slot `my`)
+    const int owner = (int)(q / pv.Qown);
+    out = reinterpret_cast<int32_t*>(pv.base[owner] + pv.off_cnt) + ((int64_t)pv.my * pv.Qown + (q - (int64_t)owner * pv.Qown)) * stride;
+  }
   const int nj = n_junk[q];
   int Rtot = 0;
   for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
@@ -686,8 +698,9 @@ __global__ void __launch_bounds__(kCountThreads, 6)
 rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int G, int64_t g_offset, int shards, int cap,
                   int out_cap, int Rp, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                   const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
-                  unsigned long long* __restrict__ ties_out) {
+                  unsigned long long* __restrict__ ties_out, const PeerView pv) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
+  if (pv.shards) peer_signal_and_wait(pv, 0);
   const CountSmemPlan plan = count_smem_plan(Rp);
   uint64_t* T = reinterpret_cast<uint64_t*>(cs_raw);
   int32_t* hist = reinterpret_cast<int32_t*>(cs_raw + plan.hist_off);
@@ -698,6 +711,10 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   const int tid = threadIdx.x;
   const int stride = out_cap + 2;
   int32_t* out = counts + q * stride;
+  if (pv.shards) {
+    const int owner = (int)(q / pv.Qown);
+    out = reinterpret_cast<int32_t*>(pv.base[owner] + pv.off_cnt) + ((int64_t)pv.my * pv.Qown + (q - (int64_t)owner * pv.Qown)) * stride;
+  }
   int Rtot = 0;
   for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
   if (tid == 0 && ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
@@ -868,8 +885,9 @@ size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(m
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
-               int32_t* counts, unsigned long long* ties, cudaStream_t stream) {
-  IEEE_REQUIRE(distmat && rel_all && n_rel && junk && n_junk && counts, "rank_count: null pointer");
+               int32_t* counts, unsigned long long* ties, cudaStream_t stream, const PeerView* peers) {
+  const PeerView pv = peers ? *peers : no_peers();
+  IEEE_REQUIRE(distmat && rel_all && n_rel && junk && n_junk && (counts || pv.shards), "rank_count: null pointer");
   IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && shards >= 1 && cap >= 1 && out_cap >= 0,
                "rank_count: bad shape");
   if (Q == 0) return IEEE_OK;
@@ -883,7 +901,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
     else IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<1>, wsmem);
     const unsigned grid = team ? (unsigned)Q : (unsigned)((Q + kWarpQ - 1) / kWarpQ);
     kern<<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel,
-                                               junk, n_junk, counts, ties);
+                                               junk, n_junk, counts, ties, pv);
     count_launch();
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
@@ -893,7 +911,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   IEEE_REQUIRE(smem <= 200 * 1024, "rank_count: %d relevant items per query exceed the shared-memory budget", out_cap);
   IEEE_ENSURE_DYN_SMEM(rank_count_kernel, smem);
   rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, Rp, rel_all,
-                                                                  n_rel, junk, n_junk, counts, ties);
+                                                                  n_rel, junk, n_junk, counts, ties, pv);
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -901,8 +919,9 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
 
 int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
                 const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel, int32_t* n_rel,
-                uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream) {
-  IEEE_REQUIRE(distmat && q_pids && q_camids && g_camids && group && rel && n_rel && junk && n_junk && overflow,
+                uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream, const PeerView* peers) {
+  const PeerView pv = peers ? *peers : no_peers();
+  IEEE_REQUIRE(distmat && q_pids && q_camids && g_camids && group && (rel || pv.shards) && n_rel && junk && n_junk && overflow,
                "rank_gather: null pointer");
   IEEE_REQUIRE(Q >= 0 && G > 0 && ld >= G && cap >= 1, "rank_gather: bad shape");
   IEEE_REQUIRE(g_offset >= 0 && g_offset + G <= (int64_t(1) << 32), "rank_gather: global gallery index must fit 32 bits");
@@ -910,7 +929,7 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
   GroupView v = group_view(group, G);
   rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.keys, v.cnt,
                                                                   v.off, v.members, v.T, g_offset, cap, rel, n_rel, junk, n_junk,
-                                                                  overflow);
+                                                                  overflow, pv);
   count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -944,13 +963,64 @@ __global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restri
   is_short[q] = kept < max_rank ? 1 : 0;
 }
 
+// Peer exchange, middle stage: this rank OWNS queries [my * Qown, (my + 1) * Qown) of the block.  It sums the partial
+// counts the shards stored into its table (integers: exact in any order), derives AP / first hit / mINP term exactly
+// as rank_query_kernel does, and stores the per-query results into EVERY rank's result arrays, so that each rank can
+// run the same deterministic reduction and end with bit-identical (cmc, mAP).
+__global__ void __launch_bounds__(128) rank_owner_metrics_kernel(const PeerView pv, int64_t G_total, int max_rank,
+                                                                  const unsigned long long* __restrict__ local_stats) {
+  peer_signal_and_wait(pv, 1, local_stats);       // every shard's partial counts (and statistics) have landed here
+  const int64_t ql = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t q = (int64_t)pv.my * pv.Qown + ql;
+  if (ql >= pv.Qown || q >= pv.Qb) return;
+  const int stride = pv.W + 2;
+  const int32_t* part = reinterpret_cast<const int32_t*>(pv.base[pv.my] + pv.off_cnt) + ql * stride;
+  const int64_t shard_stride = (int64_t)pv.Qown * stride;
+  int R = 0, nj = 0;
+  for (int s = 0; s < pv.shards; ++s) { R += part[s * shard_stride + stride - 2]; nj += part[s * shard_stride + stride - 1]; }
+  double ap = 0.0, inp = 0.0;
+  int32_t first = -1, is_short = 0;
+  if (R > 0 && R <= pv.W) {                       // (R > W: rows too narrow, flagged through the statistics; rerun)
+    double acc = 0.0;
+    int pos = 0;
+    for (int k = 0; k < R; ++k) {
+      pos = 0;
+      for (int s = 0; s < pv.shards; ++s) pos += part[s * shard_stride + k];
+      if (k == 0) first = pos;
+      acc += (double)(k + 1) / ((double)pos + 1.0);          // rank.py:155-160
+    }
+    ap = acc / (double)R;
+    inp = (double)R / ((double)pos + 1.0);                   // hardest relevant item: the last (largest) position
+    is_short = (G_total - (int64_t)nj) < max_rank ? 1 : 0;
+  }
+  const int64_t gq = pv.q_base + q;
+  for (int p = 0; p < pv.shards; ++p) {
+    reinterpret_cast<double*>(pv.base[p] + pv.off_ap)[gq] = ap;
+    reinterpret_cast<double*>(pv.base[p] + pv.off_inp)[gq] = inp;
+    reinterpret_cast<int32_t*>(pv.base[p] + pv.off_first)[gq] = first;
+    reinterpret_cast<int32_t*>(pv.base[p] + pv.off_short)[gq] = is_short;
+  }
+}
+
+int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
+                       cudaStream_t stream) {
+  IEEE_REQUIRE(peers && peers->shards >= 1 && local_stats, "rank_owner_metrics: needs a peer exchange");
+  if (max_rank > G_total) max_rank = (int32_t)G_total;
+  rank_owner_metrics_kernel<<<(unsigned)((peers->Qown + 127) / 128), 128, 0, stream>>>(*peers, G_total, max_rank, local_stats);
+  count_launch();
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
 __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restrict__ ap, const int32_t* __restrict__ first,
                                                             const int32_t* __restrict__ is_short, int64_t Q, int max_rank,
                                                             const unsigned long long* __restrict__ ties, float* __restrict__ cmc,
                                                             ieee_eval_summary* __restrict__ summary,
                                                             const double* __restrict__ inp,
-                                                            const int32_t* __restrict__ overflow) {
+                                                            const int32_t* __restrict__ overflow, const PeerView pv,
+                                                            long long* __restrict__ stats_out) {
   extern __shared__ __align__(16) uint8_t rs_raw[];
+  if (pv.shards) peer_signal_and_wait(pv, 2);      // every owner's per-query results have landed in this rank's arrays
   double* sd = reinterpret_cast<double*>(rs_raw);                 // [1024] AP partial sums
   double* si = sd + 1024;                                         // [1024] INP partial sums
   int32_t* hfirst = reinterpret_cast<int32_t*>(si + 1024);        // [max_rank + 1]
@@ -1000,11 +1070,23 @@ __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restr
     summary->sum_ap = sd[0];
     summary->mAP = valid > 0 ? sd[0] / (double)valid : 0.0;
     summary->num_valid = valid;
-    summary->num_ties = ties ? (int64_t)*ties : 0;
+    long long n_ties = ties ? (long long)*ties : 0, over = overflow ? (long long)*overflow : 0;
+    if (pv.shards) {   // statistics of all shards (written into this rank's header with the phase-B hand-over)
+      const long long* st = reinterpret_cast<const long long*>(pv.base[pv.my] + 512);
+      long long longest = 0;
+      n_ties = 0; over = 0;
+      for (int s = 0; s < pv.shards; ++s) {
+        over = max(over, (long long)(int32_t)st[4 * s]);
+        n_ties += st[4 * s + 1];
+        longest = max(longest, st[4 * s + 2]);
+      }
+      if (stats_out) { stats_out[0] = over; stats_out[1] = n_ties; stats_out[2] = longest; }
+    }
+    summary->num_ties = n_ties;
     summary->num_short = s_short;
     summary->max_rank = max_rank;
     summary->status = valid == 0 ? IEEE_ERR_NO_VALID_QUERY : (s_short > 0 ? IEEE_ERR_SHORT_RANK_LIST : IEEE_OK);
-    summary->list_overflow = overflow ? (int64_t)*overflow : 0;
+    summary->list_overflow = over;
     summary->mINP = (inp && valid > 0) ? si[0] / (double)valid : 0.0;
   }
 }
@@ -1025,12 +1107,14 @@ int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_
 
 int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_list, int64_t Q, int32_t max_rank,
                 const unsigned long long* ties, float* cmc, ieee_eval_summary* summary, const double* inp,
-                const int32_t* overflow, cudaStream_t stream) {
+                const int32_t* overflow, cudaStream_t stream, const PeerView* peers, long long* stats_out) {
+  const PeerView pv = peers ? *peers : no_peers();
   IEEE_REQUIRE(ap && first && short_list && cmc && summary, "rank_reduce: null pointer");
   IEEE_REQUIRE(Q > 0 && max_rank >= 1 && max_rank <= 8192, "rank_reduce: bad shape (max_rank=%d)", max_rank);
   const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
   IEEE_ENSURE_DYN_SMEM(rank_reduce_kernel, smem);
-  rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, overflow); count_launch();
+  rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, overflow, pv, stats_out);
+  count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -1048,7 +1132,7 @@ int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t sha
   double* inp = reinterpret_cast<double*>(w + align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4));
   int rc = rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, is_short, inp, stream);
   if (rc) return rc;
-  return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, inp, overflow, stream);
+  return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, inp, overflow, stream, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -221,7 +221,7 @@ class RetrievalEvaluator:
 
     def __init__(self, gf: torch.Tensor, g_pids, g_camids, dist_metric: str = "euclidean", normalize_feature: bool = False,
                  precision: str | None = None, max_rank: int = 20, group=None, g_offset: int = 0, g_total: int | None = None,
-                 block_bytes: int = DEFAULT_BLOCK_BYTES, center: torch.Tensor | None = None):
+                 block_bytes: int = DEFAULT_BLOCK_BYTES, center: torch.Tensor | None = None, exchange: str | None = None):
         _lib.require_cuda()
         if dist_metric not in _lib.METRICS:
             raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(dist_metric))
@@ -233,6 +233,10 @@ class RetrievalEvaluator:
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.g_offset = g_offset
         self.block_bytes = block_bytes
+        # how the ranks of a sharded gallery exchange lists and counts: "peer" = stores into NVLink peer memory from
+        # inside the rank kernels (NCCL process groups), "nccl" = all-gather + all-reduce launches (any backend)
+        self.exchange = exchange or os.environ.get("IEEE_B200_EXCHANGE") or (
+            "peer" if self.world > 1 and torch.distributed.get_backend(group) == "nccl" else "nccl")
         if gf is not None:
             gf = _as_features(gf)
         # Euclidean operands are packed relative to a common centre (PackedFeatures).  It is taken from the QUERY set:
@@ -367,6 +371,27 @@ class RetrievalEvaluator:
                               idx[s:e].data_ptr(), val[s:e].data_ptr(), _lib.stream())
         return idx, val
 
+    def _rank_block_peer(self, dist, qp, qc, link, Qb_max, Qtot, q_base, cap, W, stats):
+        """gather -> count -> owner metrics of one query block with the exchanges as stores into peer memory."""
+        Qb = dist.shape[0]
+        ex = link.descriptor(Qb_max, Qb, Qtot, q_base, cap, W, link.next_epoch())
+        junk = torch.empty((Qb, cap), dtype=torch.int64, device=self.device)
+        n_rel = torch.empty(Qb, dtype=torch.int32, device=self.device)
+        n_junk = torch.empty(Qb, dtype=torch.int32, device=self.device)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.labels.ready)
+        st = cur.cuda_stream
+        _lib.call("ieee_rank_gather_peer", dist.data_ptr(), dist.stride(0), self.G, qp.data_ptr(), qc.data_ptr(),
+                  self.labels.camids.data_ptr(), self.labels.group.data_ptr(), self.g_offset, n_rel.data_ptr(), junk.data_ptr(),
+                  n_junk.data_ptr(), stats.data_ptr(), C.byref(ex), st)
+        TRACE.mark("  gather (lists stored into every peer)")
+        _lib.call("ieee_rank_count_peer", dist.data_ptr(), dist.stride(0), self.G, self.g_offset, n_rel.data_ptr(),
+                  junk.data_ptr(), n_junk.data_ptr(), stats.data_ptr(), C.byref(ex), st)
+        TRACE.mark("  count (partial counts stored into the owners)")
+        _lib.call("ieee_rank_owner_metrics_peer", self.g_total, self.max_rank, stats.data_ptr(), C.byref(ex), st)
+        TRACE.mark("  owner metrics (results stored into every peer)")
+        return ex
+
     def _rank_block(self, dist, qp, qc, cap, width, ap, first, short, ties, inp):
         Qb = dist.shape[0]
         st = _stages_for(Qb, cap, self.world, self.device, width)
@@ -467,6 +492,61 @@ class RetrievalEvaluator:
             info["distmat"] = self._block[:Q].clone()
         return cmc_host, float(summary.mAP), info
 
+    def _evaluate_one_call_peer(self, qf, q_pids, q_camids, return_distmat, cap, width, memo_key):
+        """Sharded gallery, sizes known from an earlier evaluation with the same labels: ONE foreign call enqueues the
+        whole step (ieee_retrieve_eval_prepared_peer) -- no collective launch, no host round trip before the result."""
+        from .peer import link_for
+        with torch.cuda.device(self.device):
+            lib = _lib.load()
+            Q, D = qf.shape
+            if qf.stride(1) != 1:
+                qf = qf.contiguous()
+            qp = _as_device(q_pids, torch.int64, self.device)
+            qc = _as_device(q_camids, torch.int64, self.device)
+            W = min(width, self.world * cap)
+            k_eff = min(self.max_rank, self.g_total)
+            prec = _lib.PRECISIONS[self.precision]
+            link = link_for(self.group, self.device, lib.ieee_peer_exchange_bytes(Q, Q, cap, W, self.world))
+            ex = link.descriptor(Q, Q, Q, 0, cap, W, link.next_epoch())
+            key = ("peer", Q, D, prec, cap, k_eff, str(self.device))
+            buf = _FUSED_POOL.get(key)
+            if buf is None:
+                if len(_FUSED_POOL) > 8:
+                    _FUSED_POOL.clear()
+                ws = torch.empty(lib.ieee_retrieve_prepared_peer_workspace_bytes(Q, D, prec, cap), dtype=torch.uint8, device=self.device)
+                res = torch.empty(32 + 64 + 4 * k_eff, dtype=torch.uint8, device=self.device)
+                buf = _FUSED_POOL[key] = (ws, res, torch.empty(res.shape, dtype=torch.uint8, pin_memory=True))
+            ws, res, res_host = buf
+            self._ensure_block(Q)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.labels.ready)
+            gpk = self.chunks[0][1]
+            _lib.call("ieee_retrieve_eval_prepared_peer", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
+                      _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
+                      _lib.ptr(self.center), self.G, self.g_total, self.g_offset, qp.data_ptr(), qc.data_ptr(),
+                      self.labels.camids.data_ptr(), self.max_rank, self._block.data_ptr(), self._block.stride(0),
+                      res.data_ptr() + 96, res.data_ptr() + 32, res.data_ptr(), C.byref(ex), ws.data_ptr(), ws.numel(),
+                      cur.cuda_stream)
+            res_host.copy_(res, non_blocking=True)
+            cur.synchronize()
+            out = res_host.numpy()
+            overflow, _, longest = (int(v) for v in out[:32].view(np.int64)[:3])
+            if overflow or longest > W:
+                _memo_drop(memo_key)             # sizes no longer fit these labels: size again, collectively
+                return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False, one_call=False)
+            summary = _lib.EvalSummary.from_buffer_copy(out[32:96].tobytes())
+            cmc_host = out[96:].view(np.float32).copy()
+            offs = [lib.ieee_peer_result_offset(i, Q, Q, cap, W, self.world) for i in (0, 1)]
+            # every rank holds all per-query results; copied out because the next evaluation overwrites the buffer
+            ap = link.view[offs[0]: offs[0] + 8 * Q].view(torch.float64).clone()
+            first = link.view[offs[1]: offs[1] + 4 * Q].view(torch.int32).clone()
+        raise_for_status(summary, self.max_rank)
+        info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first,
+                "mINP": float(summary.mINP)}
+        if return_distmat:
+            info["distmat"] = self._block[:Q].clone()
+        return cmc_host, float(summary.mAP), info
+
     def evaluate(self, qf: torch.Tensor, q_pids, q_camids, return_distmat: bool = False, use_cap_memo: bool = True,
                  one_call: bool | None = None):
         """Returns (cmc float32 ndarray [K'], mAP float, info dict).  Queries are replicated on every rank.
@@ -484,6 +564,14 @@ class RetrievalEvaluator:
         if (one_call and self.world == 1 and qf.is_cuda and self._host_gallery is None and len(self.chunks) == 1
                 and isinstance(self.chunks[0][1], PackedFeatures) and 0 < qf.shape[0] <= self._block_rows(qf.shape[0])):
             return self._evaluate_one_call(qf, q_pids, q_camids, return_distmat, use_cap_memo)
+        if (one_call and use_cap_memo and self.world > 1 and self.exchange == "peer" and qf.is_cuda and self._host_gallery is None
+                and len(self.chunks) == 1 and isinstance(self.chunks[0][1], PackedFeatures)
+                and 0 < qf.shape[0] <= self._block_rows(qf.shape[0]) and self._label_keys[0] is not None
+                and _tensor_key(q_pids) is not None):
+            memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
+            cap, width = _CAP_MEMO.get(memo_key, (None, 0))
+            if cap is not None and width > 0:
+                return self._evaluate_one_call_peer(qf, q_pids, q_camids, return_distmat, cap, width, memo_key)
         with torch.cuda.device(self.device):
             TRACE.mark("evaluate: start")
             Q = qf.shape[0]
@@ -578,24 +666,48 @@ class RetrievalEvaluator:
                     dist_.all_reduce(cap_t, op=dist_.ReduceOp.MAX, group=self.group)
                     cap = int(cap_t.item())
             full = None
-            for s in range(0, Q, rows):
-                e = min(Q, s + rows)
-                if s > 0:
-                    dist = contraction(s, e)
-                self._rank_block(dist, qp[s:e], qc[s:e], cap, width, ap[s:e], first[s:e], short[s:e], ties, inp[s:e])
-                if return_distmat:
-                    full = dist.clone() if full is None else torch.cat([full, dist], 0)
-            if self.world > 1:
-                import torch.distributed as dist_
-                dist_.all_reduce(ties[:2], group=self.group)      # [2] (longest merged list) is the same on every rank
+            peer = self.world > 1 and self.exchange == "peer" and Q > 0
             summ, cmc = res[32:96], res[96:].view(torch.float32)
-            TRACE.mark("rank stages done")
-            _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr() + 8,
-                      cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
+            if peer:
+                from .peer import link_for
+                lib = _lib.load()
+                W = min(width, self.world * cap) if width > 0 else self.world * cap
+                link = link_for(self.group, self.device, lib.ieee_peer_exchange_bytes(rows, Q, cap, W, self.world))
+                stats = torch.zeros(4, dtype=torch.int64, device=self.device)      # this rank's own statistics
+                ex = None
+                for s in range(0, Q, rows):
+                    e = min(Q, s + rows)
+                    if s > 0:
+                        dist = contraction(s, e)
+                    ex = self._rank_block_peer(dist, qp[s:e], qc[s:e], link, rows, Q, s, cap, W, stats)
+                    if return_distmat:
+                        full = dist.clone() if full is None else torch.cat([full, dist], 0)
+                TRACE.mark("rank stages done")
+                _lib.call("ieee_rank_reduce_peer", k_eff, cmc.data_ptr(), summ.data_ptr(), ties.data_ptr(), C.byref(ex),
+                          _lib.stream())
+                offs = [lib.ieee_peer_result_offset(i, rows, Q, cap, W, self.world) for i in (0, 1)]
+                ap = link.view[offs[0]: offs[0] + 8 * Q].view(torch.float64)       # every rank holds all per-query results
+                first = link.view[offs[1]: offs[1] + 4 * Q].view(torch.int32)
+            else:
+                for s in range(0, Q, rows):
+                    e = min(Q, s + rows)
+                    if s > 0:
+                        dist = contraction(s, e)
+                    self._rank_block(dist, qp[s:e], qc[s:e], cap, width, ap[s:e], first[s:e], short[s:e], ties, inp[s:e])
+                    if return_distmat:
+                        full = dist.clone() if full is None else torch.cat([full, dist], 0)
+                if self.world > 1:
+                    import torch.distributed as dist_
+                    dist_.all_reduce(ties[:2], group=self.group)      # [2] (longest merged list) is the same on every rank
+                TRACE.mark("rank stages done")
+                _lib.call("ieee_rank_reduce", ap.data_ptr(), first.data_ptr(), short.data_ptr(), Q, k_eff, ties.data_ptr() + 8,
+                          cmc.data_ptr(), summ.data_ptr(), inp.data_ptr(), _lib.stream())
             TRACE.mark("reduce done")
             host = _result_buffer(self.device, res.numel())                    # pinned landing zone
             host.copy_(res, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            if peer:
+                ap, first = ap.clone(), first.clone()    # the exchange buffer is overwritten by the next evaluation
             out = host.numpy()
             overflow, _, longest = (int(v) for v in out[:32].view(np.int64)[:3])
             summary = _lib.EvalSummary.from_buffer_copy(out[32:96].tobytes())

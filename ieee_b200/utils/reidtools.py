@@ -97,7 +97,7 @@ def visualize_ranked_results(distmat, dataset, data_type, width=128, height=256,
     query, gallery = dataset
     assert num_q == len(query)
     assert num_g == len(gallery)
-    idx, matched = ranked_lists(distmat, dataset, topk, ranked)
+    idx, matched = ranked_lists(distmat, dataset, topk) if ranked is None else ranked_lists(distmat, dataset, topk, ranked)
     as_image = data_type == 'image'
     if as_image:
         import cv2

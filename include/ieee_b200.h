@@ -298,6 +298,71 @@ int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq
                 int64_t Q, int64_t G, int32_t k1, int32_t k2, double lambda_value, float* out, int64_t ldo,
                 void* workspace, size_t workspace_bytes, ieee_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Peer exchange: the two exchange steps of a gallery sharded over the GPUs of one box (relevant lists to every rank,
+ * partial counts back) as STORES into NVLink peer memory from inside the rank kernels, with flag words for the
+ * hand-over -- no collective launches between the kernels of a step.
+ *
+ * Every rank allocates one exchange buffer (ieee_peer_alloc: cudaMalloc, zeroed, plus its 64-byte cudaIpc handle),
+ * the handles are exchanged once through the host (any process group), every rank maps its peers' buffers
+ * (ieee_peer_open).  Per query block all ranks then call, with identical Qb / cap / W / epoch and their own my_shard:
+ *
+ *   ieee_rank_gather_peer         lists of this shard -> slot my_shard of EVERY rank's list table
+ *   ieee_rank_count_peer          waits for all lists; streams the local rows; partial counts -> the OWNER of each query
+ *                                 (queries of a block are owned in contiguous slices of ceil(Qb / shards))
+ *   ieee_rank_owner_metrics_peer  waits for all partial counts of the owned queries; sums them (integers: exact in any
+ *                                 order); AP / first hit / mINP term -> EVERY rank's per-query result arrays
+ * and once per evaluation
+ *   ieee_rank_reduce_peer         waits for all results; the same fixed-tree reduction on every rank: bit-identical
+ *                                 (cmc, summary) everywhere; stats_out (int64[3], device, may be NULL) receives
+ *                                 {list overflow (needed capacity or 0), tie pairs, longest merged list} over all shards.
+ * A kernel that waits spins on flags in its OWN buffer (bounded: it traps after ~4 s); it never waits for a kernel of
+ * the same rank that is queued behind it, so the ranks cannot deadlock as long as all of them issue the same calls.
+ * `epoch` must grow by one per query block (never reuse a value with the same buffers).
+ * ---------------------------------------------------------------------------------------------- */
+#define IEEE_MAX_PEERS 16
+typedef struct {
+  int32_t shards, my_shard;
+  uint64_t epoch;
+  void* base[IEEE_MAX_PEERS]; /* exchange buffer of every shard as mapped into THIS process (base[my_shard]: own) */
+  int64_t Qb_max, Qb, Qtot, q_base; /* rows of the largest block (sizes the buffer); rows of this block; rows of the
+                                       whole evaluation; first row of this block */
+  int32_t cap, W;             /* per-shard list capacity; count-row width (>= longest merged list, <= shards * cap) */
+} ieee_peer_exchange;
+
+size_t ieee_peer_exchange_bytes(int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards);
+int ieee_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_out /* 64 bytes, host */);
+int ieee_peer_open(const void* ipc_handle /* 64 bytes, host */, void** ptr);
+int ieee_peer_close(void* ptr);
+int ieee_peer_free(void* ptr);
+/* stats: uint64[4] of device memory private to this rank, zeroed by the caller once per evaluation:
+ * [0] gather overflow (int32), [1] tie pairs, [2] longest merged list. */
+int ieee_rank_gather_peer(const float* distmat, int64_t ld, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                          const int64_t* g_camids, const void* group, int64_t g_offset, int32_t* n_rel, uint64_t* junk,
+                          int32_t* n_junk, unsigned long long* stats, const ieee_peer_exchange* ex, ieee_stream_t stream);
+int ieee_rank_count_peer(const float* distmat, int64_t ld, int64_t G, int64_t g_offset, const int32_t* n_rel,
+                         const uint64_t* junk, const int32_t* n_junk, unsigned long long* stats,
+                         const ieee_peer_exchange* ex, ieee_stream_t stream);
+int ieee_rank_owner_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats,
+                                 const ieee_peer_exchange* ex, ieee_stream_t stream);
+int ieee_rank_reduce_peer(int32_t max_rank, float* cmc, ieee_eval_summary* summary, int64_t* stats_out,
+                          const ieee_peer_exchange* ex, ieee_stream_t stream);
+/* One query block of a sharded evaluation in ONE call (the sharded counterpart of ieee_retrieve_eval_prepared): pack the
+ * queries -> contraction against this rank's packed gallery slice -> gather / count / owner metrics / reduce with the
+ * peer exchange.  `ex` describes one block of Q rows (Qb == Qtot == Q, q_base == 0) with the list capacity and row width
+ * every rank agreed on; G_total / g_offset place the slice in the whole gallery.  stats_out as in ieee_rank_reduce_peer:
+ * stats_out[0] != 0 or stats_out[2] > ex->W mean the sizes were too small and the call must be repeated with larger ones. */
+size_t ieee_retrieve_prepared_peer_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap);
+int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,
+                                     int precision, const void* g_packed, const void* group, const float* center, int64_t G,
+                                     int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
+                                     const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
+                                     ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
+                                     void* workspace, size_t workspace_bytes, ieee_stream_t stream);
+/* Byte offset of a per-query result array inside an exchange buffer: which = 0 AP (double[Qtot]), 1 first hit
+ * (int32[Qtot]), 2 mINP term (double[Qtot]), 3 short-list flag (int32[Qtot]). */
+size_t ieee_peer_result_offset(int which, int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards);
+
 #ifdef __cplusplus
 }
 #endif

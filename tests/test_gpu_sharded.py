@@ -83,6 +83,79 @@ def test_topk_merge_across_shards():
     assert np.array_equal(idx.cpu().numpy(), idx_o) and np.array_equal(val.cpu().numpy(), val_o)
 
 
+@pytest.mark.parametrize("shards", [1, 2, 3])
+def test_peer_exchange_protocol_on_one_gpu(shards):
+    """The peer-memory exchange (ieee_rank_*_peer) with `shards` virtual ranks on ONE device: one buffer and one stream
+    per virtual rank, kernels of different ranks handing over through the flag words exactly as they do across GPUs.
+    Two query blocks of different size, so that epochs, block offsets and owner slices are all exercised."""
+    import ctypes as C
+    from ieee_b200.peer import LocalPeers
+    s = make_retrieval_set(150, 1203, 20, 4, dim=64, sigma=2.0, seed=40 + shards)
+    d = R.compute_distance_matrix(s.qf, s.gf).numpy()
+    d[:, ::3] = np.round(d[:, ::3])                                  # ties, also across shard boundaries
+    cmc_o, map_o, info = R.eval_market1501(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids, 20, return_info=True)
+    pos = R.kept_positions(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    dev = torch.device("cuda")
+    lib = _lib.load()
+    Q, G = d.shape
+    qp, qc = torch.from_numpy(s.q_pids).to(dev), torch.from_numpy(s.q_camids).to(dev)
+    parts = []
+    for r in range(shards):
+        g0, g1 = shard_bounds(G, shards, r)
+        dl = torch.from_numpy(np.ascontiguousarray(d[:, g0:g1])).to(dev)
+        parts.append((g0, g1, dl, GalleryLabels(s.g_pids[g0:g1], s.g_camids[g0:g1], dev)))
+    cap = max(p[3].list_cap(qp) for p in parts)
+    W = min(shards * cap, max(p.size for p in pos))
+    Qb_max = 96
+    peers = LocalPeers(shards, dev, lib.ieee_peer_exchange_bytes(Qb_max, Q, cap, W, shards))
+    streams = [torch.cuda.Stream() for _ in range(shards)]
+    stats = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(shards)]
+    keep = []
+    torch.cuda.synchronize()
+    epoch = 0
+    for q0 in range(0, Q, Qb_max):
+        q1 = min(Q, q0 + Qb_max)
+        Qb = q1 - q0
+        epoch += 1
+        for r, (g0, g1, dl, gal) in enumerate(parts):
+            ex = peers.descriptor(r, Qb_max, Qb, Q, q0, cap, W, epoch)
+            junk = torch.empty((Qb, cap), dtype=torch.int64, device=dev)
+            n_rel, n_junk = torch.empty(Qb, dtype=torch.int32, device=dev), torch.empty(Qb, dtype=torch.int32, device=dev)
+            keep.append((junk, n_rel, n_junk))
+            blk = dl[q0:q1]
+            with torch.cuda.stream(streams[r]):
+                st = streams[r].cuda_stream
+                _lib.call("ieee_rank_gather_peer", blk.data_ptr(), blk.stride(0), g1 - g0, qp[q0:q1].data_ptr(), qc[q0:q1].data_ptr(),
+                          gal.camids.data_ptr(), gal.group.data_ptr(), g0, n_rel.data_ptr(), junk.data_ptr(), n_junk.data_ptr(),
+                          stats[r].data_ptr(), C.byref(ex), st)
+                _lib.call("ieee_rank_count_peer", blk.data_ptr(), blk.stride(0), g1 - g0, g0, n_rel.data_ptr(), junk.data_ptr(),
+                          n_junk.data_ptr(), stats[r].data_ptr(), C.byref(ex), st)
+                _lib.call("ieee_rank_owner_metrics_peer", G, 20, stats[r].data_ptr(), C.byref(ex), st)
+    results = []
+    for r in range(shards):
+        ex = peers.descriptor(r, Qb_max, Q - (Q - 1) // Qb_max * Qb_max, Q, (Q - 1) // Qb_max * Qb_max, cap, W, epoch)
+        cmc = torch.empty(20, dtype=torch.float32, device=dev)
+        summ = torch.empty(64, dtype=torch.uint8, device=dev)
+        st_out = torch.zeros(4, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(streams[r]):
+            _lib.call("ieee_rank_reduce_peer", 20, cmc.data_ptr(), summ.data_ptr(), st_out.data_ptr(), C.byref(ex),
+                      streams[r].cuda_stream)
+        results.append((cmc, summ, st_out))
+    torch.cuda.synchronize()
+    off_ap, off_first = (lib.ieee_peer_result_offset(i, Qb_max, Q, cap, W, shards) for i in (0, 1))
+    ap_o = np.array([((np.arange(p.size) + 1.0) / (p + 1.0)).sum() / p.size if p.size else 0.0 for p in pos])
+    for r, (cmc, summ, st_out) in enumerate(results):
+        summary = _lib.EvalSummary.from_buffer_copy(summ.cpu().numpy().tobytes())
+        assert np.array_equal(cmc.cpu().numpy(), cmc_o) and abs(summary.mAP - map_o) < 1e-9 and summary.list_overflow == 0
+        over, ties, longest = st_out.cpu().numpy()[:3]
+        assert over == 0 and longest == max(p.size for p in pos) and summary.num_ties == ties
+        ap = peers.views[r][off_ap: off_ap + 8 * Q].view(torch.float64).cpu().numpy()
+        first = peers.views[r][off_first: off_first + 4 * Q].view(torch.int32).cpu().numpy()
+        assert np.abs(ap - ap_o).max() < 1e-12 and np.array_equal(first, info["first_hit"])
+    assert all(results[0][1].cpu().numpy().tobytes() == x[1].cpu().numpy().tobytes() for x in results)   # bit-identical
+    peers.free()
+
+
 def _tied_set():
     """Gallery with rows duplicated ACROSS the two shards: bit-equal distances on different ranks, so the merged order
     depends on the global-index tie rule."""
@@ -160,8 +233,19 @@ def _nccl_worker(rank, world, port, out):
     s = make_retrieval_set(500, 3001, 40, 4, dim=256, sigma=2.5, seed=17, distractor_frac=0.1)
     g0, g1 = shard_bounds(3001, world, rank)
     ev = RetrievalEvaluator(s.gf[g0:g1].cuda(), s.g_pids[g0:g1], s.g_camids[g0:g1], group=dist.group.WORLD, g_offset=g0,
-                            g_total=3001)
+                            g_total=3001, block_bytes=256 * (g1 - g0) * 4)                     # two query blocks
+    assert ev.exchange == "peer"
     cmc, mAP, info = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids, return_distmat=True)
+    # the NCCL exchange (all-gather + all-reduce launches) and the peer-memory exchange agree to the last bit,
+    # twice in a row (second time: capacity memo hit, narrower count rows, next epochs)
+    ev_n = RetrievalEvaluator(s.gf[g0:g1].cuda(), s.g_pids[g0:g1], s.g_camids[g0:g1], group=dist.group.WORLD, g_offset=g0,
+                              g_total=3001, exchange="nccl", center=ev.center)
+    for _ in range(2):
+        c_n, m_n, i_n = ev_n.evaluate(s.qf.cuda(), s.q_pids, s.q_camids)
+        c_p, m_p, i_p = ev.evaluate(s.qf.cuda(), s.q_pids, s.q_camids)
+        assert np.array_equal(c_n, c_p) and m_n == m_p and i_n["num_ties"] == i_p["num_ties"] and i_n["mINP"] == i_p["mINP"]
+        assert torch.equal(i_n["ap"], i_p["ap"]) and torch.equal(i_n["first"], i_p["first"])
+    assert np.array_equal(c_p, cmc) and m_p == mAP
     gathered = [torch.empty((500, shard_bounds(3001, world, r)[1] - shard_bounds(3001, world, r)[0]), device="cuda") for r in range(world)]
     dist.all_gather(gathered, info["distmat"].contiguous())
     if rank == 0:
