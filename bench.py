@@ -430,8 +430,10 @@ def run_ours(args):
             dist.barrier(group=group)
         torch.cuda.synchronize()
 
+    last_ev = [None]
+
     def step_device(qf, gf, qp, qc, gp, gc):
-        ev = RetrievalEvaluator(gf, gp, gc, "euclidean", False, None, MAX_RANK, group=group, g_offset=g0, g_total=G_TOTAL)
+        ev = last_ev[0] = RetrievalEvaluator(gf, gp, gc, "euclidean", False, None, MAX_RANK, group=group, g_offset=g0, g_total=G_TOTAL)
         return ev.evaluate(qf, qp, qc)
 
     def step_e2e():
@@ -469,6 +471,9 @@ def run_ours(args):
     ms_dev, launches, clocks, out = timed(lambda: step_device(qf_d, gf_d, *lab_d), args.steps, args.warmup)
     cmc, mAP, info = out
     value = Q * args.steps / (ms_dev / 1e3)
+    count_path = ("fused into the contraction's epilogue (no distance block): %d of %d 128-output spans spilled for the exact recount"
+                  % (last_ev[0].fused_stats["spilled_spans"], last_ev[0].fused_stats["spans"])) if info.get("fused") else (
+        "staged: distance block written, gathered, counted (rank_count_warp_kernel)")
 
     # ---- end to end: pinned host buffers in, (cmc, mAP) on the host out ---------------------------------
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
@@ -496,7 +501,7 @@ def run_ours(args):
     time_stage("distmat_f16x3", lambda: packed_distmat(holder["q"], holder["g"], dist_buf))
     time_stage("group_gallery", lambda: holder.__setitem__("lab", GalleryLabels(lab_d[2], lab_d[3], dev)))
     gal = holder["lab"]
-    cap = info["cap"]
+    cap = gal.list_cap(lab_d[0])
     st = RankStages(Q, cap, 1, dev)
     time_stage("rank_gather", lambda: st.gather(dist_buf, lab_d[0], lab_d[1], gal, g0))
     time_stage("rank_count", lambda: st.count(dist_buf, Gs, g0))
@@ -578,6 +583,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16x3 split of f32 (fp32-equivalent products, f32 accumulate); rank: u32/i32; AP: f64",
             "data": "synthetic", "config": bench_config(n_gpus),
+            "count_path": count_path,
             "exchange": ("none (one GPU)" if world == 1 else os.environ.get("IEEE_B200_EXCHANGE", "peer") +
                          (": stores into NVLink peer memory from the rank kernels, flag hand-over, no collective launches per step"
                           if os.environ.get("IEEE_B200_EXCHANGE", "peer") == "peer" else ": all-gather + all-reduce launches")),

@@ -55,6 +55,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
 void count_launch(int n = 1);
 extern int g_debug_flags;       // ieee_set_debug_flags()
+extern int g_fused_chunk_kb;    // accumulation chunk of the fused-count contraction (0 = as the store kernel)
 extern int g_raster_panel;      // ieee_set_raster_panel(): m tiles per raster panel of the contraction (0 = sized for L2)
 extern int g_accum_chunk_kb;    // ieee_set_accum_chunk(): K-slices per tensor-core accumulation chunk (0 = whole K)   // bookkeeping behind ieee_launch_count()
 
@@ -109,6 +110,25 @@ inline PackedLayout packed_layout(int64_t rows, int64_t D, int precision) {
   return L;
 }
 
+// ---- gallery grouping (rank.cu): open-addressing hash pid -> slot; members of a slot = the gallery items of that identity
+static constexpr long long kEmptyPid = (long long)0x8080808080808080ull;   // memset(0x80) pattern; not a usable pid
+struct GroupTables { const long long* keys; const int32_t* cnt; const int32_t* off; const int32_t* members; int64_t T; };
+GroupTables group_tables(const void* blob, int64_t G);
+
+// ---- counting fused into the contraction's epilogue (fused.cu, distmat_sm100.cu) ------------------------------------
+constexpr int kFusedLC = 32;             // thresholds (same-identity gallery items) per query the epilogue tables hold
+struct FusedCount {
+  const float* thr;                      // [Q][LC] approximate distance of the query to its i-th same-identity item; pad -inf
+  const int32_t* tn;                     // [Q]     number of such items
+  const float* eps;                      // [Q]     half-width of the band in which an output is NOT decided by `thr`
+  int32_t* cnt;                          // [Q][LC] outputs definitely below thr[q][i] (atomicAdd)
+  unsigned int* spill_n;                 // [1]     spans handed to the resolve kernels
+  unsigned long long* spill_meta;        // [cap]   row << 32 | first column
+  float* spill_val;                      // [cap][128]
+  uint32_t spill_cap;
+  int LC;
+};
+
 // ---- exchange between the ranks of a sharded gallery over NVLink peer memory ----------------------------------
 // Every rank owns one exchange buffer (ieee_peer_alloc) that all ranks of the gallery group map (cudaIpc): the rank
 // kernels STORE their lists / partial counts / per-query results straight into the peers' buffers and hand over with
@@ -134,6 +154,22 @@ inline PeerView no_peers() { PeerView v; memset(&v, 0, sizeof(v)); return v; }
 
 // ---- raw PTX: mbarrier / TMA / tcgen05 ----------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ uint32_t hash_pid(long long pid) {
+  uint64_t x = (uint64_t)pid;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;   // murmur3 finaliser
+  return (uint32_t)x;
+}
+// slot of `pid`, or -1 if the gallery has no such identity
+__device__ __forceinline__ int group_find(const long long* __restrict__ keys, int64_t T, long long pid) {
+  uint32_t h = hash_pid(pid) & (uint32_t)(T - 1);
+  while (true) {
+    const long long k = keys[h];
+    if (k == pid) return (int)h;
+    if (k == kEmptyPid) return -1;
+    h = (h + 1) & (uint32_t)(T - 1);
+  }
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

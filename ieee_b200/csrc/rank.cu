@@ -43,7 +43,6 @@ __host__ __device__ __forceinline__ int next_pow2(int x) {
 // grouped by identity.  Four small kernels (insert+count, allocate, fill) instead of a sort; once per gallery
 // (shard), reused by every query block.  Order inside a group is arbitrary -- the consumers sort what they take.
 // ---------------------------------------------------------------------------------------------------------
-static constexpr long long kEmptyPid = (long long)0x8080808080808080ull;   // memset(0x80) pattern; not a usable pid
 
 struct GroupView {
   long long* keys;     // [T]  pid of the slot or kEmptyPid
@@ -77,21 +76,9 @@ static inline GroupView group_view(const void* blob, int64_t G) {
   return v;
 }
 size_t gallery_group_bytes(int64_t G) { return group_view(nullptr, G).total; }
-
-__device__ __forceinline__ uint32_t hash_pid(long long pid) {
-  uint64_t x = (uint64_t)pid;
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;   // murmur3 finaliser
-  return (uint32_t)x;
-}
-// slot of `pid`, or -1 if the gallery has no such identity
-__device__ __forceinline__ int group_find(const long long* __restrict__ keys, int64_t T, long long pid) {
-  uint32_t h = hash_pid(pid) & (uint32_t)(T - 1);
-  while (true) {
-    const long long k = keys[h];
-    if (k == pid) return (int)h;
-    if (k == kEmptyPid) return -1;
-    h = (h + 1) & (uint32_t)(T - 1);
-  }
+GroupTables group_tables(const void* blob, int64_t G) {
+  const GroupView v = group_view(blob, G);
+  return GroupTables{v.keys, v.cnt, v.off, v.members, v.T};
 }
 
 __global__ void group_insert_kernel(const int64_t* __restrict__ g_pids, int64_t G, long long* keys, int32_t* cnt,
@@ -535,8 +522,20 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     out = reinterpret_cast<int32_t*>(pv.base[owner] + pv.off_cnt) + ((int64_t)pv.my * pv.Qown + (q - (int64_t)owner * pv.Qown)) * stride;
   }
   const int nj = n_junk[q];
-  int Rtot = 0;
-  for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
+  // list lengths of all shards in ONE round of loads (lane s reads shard s), then a warp scan: with 8 shards the
+  // set-up used to pay 8 dependent trips to L2 per query, and set-up is what a short (sharded) row costs
+  int Rtot = 0, my_n = 0, my_base = 0;
+  const bool lanes_cover_shards = shards <= 32;
+  if (lanes_cover_shards) {
+    if (lane < shards) my_n = (int)rel_all[((int64_t)lane * Q + q) * (cap + 1) + cap];
+    int incl = my_n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    my_base = incl - my_n;
+    Rtot = __shfl_sync(0xffffffffu, incl, 31);
+  } else {
+    for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
+  }
   if (lane == 0 && wq == 0) {
     out[stride - 1] = nj; out[stride - 2] = n_rel[q];
     // longest merged list seen: sizes the next call's rows (out_cap); a list longer than this call's is flagged by it
@@ -548,12 +547,26 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   if (wq == 0) {                             // ---- setup by the team's first warp --------------------------------
     // thresholds of all shards, staged in this warp's `priv` (not live yet)
     uint64_t* Tin = reinterpret_cast<uint64_t*>(priv);
-    int base = 0;
-    for (int s = 0; s < shards; ++s) {
-      const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
-      const int n = (int)src[cap];
-      for (int i = lane; i < n; i += 32) Tin[base + i] = src[i];
-      base += n;
+    if (lanes_cover_shards) {
+      // flattened copy: entry idx of the merged list lives in shard s at position idx - base_s; every lane finds its
+      // (s, position) with shuffles only and then issues ONE load, so all entries arrive in one round trip
+      for (int idx0 = 0; idx0 < R; idx0 += 32) {
+        const int idx = idx0 + lane;
+        int s_mine = -1, i_mine = 0;
+        for (int s = 0; s < shards; ++s) {
+          const int b = __shfl_sync(0xffffffffu, my_base, s), n = __shfl_sync(0xffffffffu, my_n, s);
+          if (idx >= b && idx < b + n) { s_mine = s; i_mine = idx - b; }
+        }
+        if (s_mine >= 0) Tin[idx] = rel_all[((int64_t)s_mine * Q + q) * (cap + 1) + i_mine];
+      }
+    } else {
+      int base = 0;
+      for (int s = 0; s < shards; ++s) {
+        const uint64_t* src = rel_all + ((int64_t)s * Q + q) * (cap + 1);
+        const int n = (int)src[cap];
+        for (int i = lane; i < n; i += 32) Tin[base + i] = src[i];
+        base += n;
+      }
     }
     __syncwarp();
     // rank sort (keys are distinct)
