@@ -28,7 +28,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 import numpy as np
@@ -65,47 +64,65 @@ def bench_config(n_gpus: int) -> dict:
                   "stage timings flush L2 with a 256 MB write between repetitions"}
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+class ClockSampler:
+    """SM clock / throttle reasons while the timed region runs, sampled by an `nvidia-smi -lms` child process (the
+    profiling recipe's clocks line): a sampling THREAD in this process would take the GIL from the loop being timed --
+    and with several ranks every rank waits for the slowest host.  Falls back to one NVML reading when nvidia-smi is
+    not on the PATH."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int, period: float = 0.01):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop_evt = threading.Event()
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-
-    def run(self):
-        if self.nv is None:
+    def __init__(self, index: int, period_ms: int = 5, enabled: bool = True):
+        self.index, self.proc = index, None
+        if not enabled:
             return
-        nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop_evt.is_set():
+        import shutil
+        import subprocess
+        exe = shutil.which("nvidia-smi")
+        if exe:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
+                self.proc = subprocess.Popen([exe, "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                              "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             except Exception:
-                pass
-            time.sleep(self.period)
+                self.proc = None
+
+    def start(self):
+        if self.proc is not None:
+            time.sleep(0.05)                      # let the child take its first readings before the region starts
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        samples, reasons, max_mhz = [], set(), None
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            for ln in out.splitlines():
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    samples.append(float(parts[0]))
+                    max_mhz = float(parts[1])
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        else:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(samples) if samples else None, "sm_max_mhz": max_mhz,
+                "reasons": sorted(reasons), "samples": len(samples), "how": "nvidia-smi -lms child process" if self.proc else "nvml, one reading"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -447,7 +464,7 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank, period=0.01 if rank == 0 else 1.0)   # rank 0 samples; the others stay quiet
+        sampler = ClockSampler(local_rank, enabled=rank == 0)      # rank 0 samples; the others stay quiet
         sampler.start()
         l0 = lib.ieee_launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ieee_eval_market1501": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
     "ieee_gallery_prepare_workspace_bytes": (sz, [i64]),
     "ieee_gallery_prepare": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, i64, vp, vp, vp, vp, vp]),
+    "ieee_eval_market1501_f64": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
     "ieee_retrieve_workspace_bytes": (sz, [i64, i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval": (C.c_int, [vp, i64, vp, i64, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32,
                                      C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),

@@ -59,6 +59,9 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
                int32_t* counts, unsigned long long* ties, cudaStream_t stream, const PeerView* peers = nullptr);
 int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
                        cudaStream_t stream);
+int rank_count_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                   const int64_t* g_camids, const void* group, int32_t cap, int32_t* counts, unsigned long long* ties,
+                   int32_t* overflow, cudaStream_t stream);
 size_t rank_finalize_workspace_bytes(int64_t Q);
 int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                        int32_t max_rank, double* ap, int32_t* first, int32_t* short_list, double* inp,
@@ -430,6 +433,44 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
   if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, center, g_packed, stream))) return rc;
   if (grouping) IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
   return IEEE_OK;
+}
+
+// float64 distance matrix: ranked in float64 order (rank.py:117 argsorts whatever dtype it is given)
+int ieee_eval_market1501_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
+                             const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
+                             int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
+                             ieee_stream_t stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IEEE_REQUIRE(distmat && q_pids && g_pids && q_camids && g_camids && cmc && summary && workspace, "eval (f64): null pointer");
+  IEEE_REQUIRE(Q > 0 && G > 0 && ld >= G && max_rank >= 1, "eval (f64): bad shape Q=%lld G=%lld ld=%lld max_rank=%d", (long long)Q,
+               (long long)G, (long long)ld, max_rank);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "eval (f64): workspace must be 256-byte aligned");
+  Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
+  void* group = a.take(gallery_group_bytes(G));
+  int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
+  if (!group || !scratch) { set_error("eval (f64): workspace too small"); return IEEE_ERR_WORKSPACE; }
+  if ((rc = gallery_group(g_pids, G, group, stream))) return rc;
+  int32_t need = 0;
+  if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
+  if (need < 1) need = 1;
+  if (cap > 0 && need > cap) {
+    set_error("eval (f64): a query has %d same-identity gallery items but list capacity is %d", need, cap);
+    return IEEE_ERR_CAPACITY;
+  }
+  cap = need;
+  int32_t* counts = static_cast<int32_t*>(a.take(size_t(Q) * (cap + 2) * 4));
+  void* fws = a.take(rank_finalize_workspace_bytes(Q));
+  if (!counts || !fws) {
+    set_error("eval (f64): workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
+              ieee_eval_workspace_bytes(Q, G, cap), cap);
+    return IEEE_ERR_WORKSPACE;
+  }
+  IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
+  unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
+  if ((rc = rank_count_f64(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, cap, counts, ties, scratch + 1, stream))) return rc;
+  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
 }
 
 // ---- retrieval + evaluation in one call ----------------------------------------------------------------

@@ -137,6 +137,7 @@ struct FusedCount {
 //   [128, 256)  flag B[s]: ... whose partial counts from shard s have landed here
 //   [256, 384)  flag C[s]: ... whose per-query results from owner s have landed here
 //   [384, 408)  sent[3]:   (local) epoch this rank has already signalled per phase
+//   [416, 440)  seen[3]:   (local) epoch for which this rank has already seen every peer's flag of the phase
 //   [512, ...)  stats[s][4]: shard s' {gather overflow, tie pairs, longest merged list, -}
 constexpr int kMaxPeers = 16;
 constexpr size_t kPeerHeaderBytes = 1024;
@@ -185,30 +186,45 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // `stats_src` (4 words, may be null) is copied into this rank's stats slot of every peer before the flags.
 // The wait is bounded like mbar_wait: a peer that never arrives traps instead of hanging the box.
 __device__ __forceinline__ void peer_signal_and_wait(const PeerView& pv, int phase, const unsigned long long* stats_src = nullptr) {
-  if (threadIdx.x == 0) {
-    unsigned long long* sent = reinterpret_cast<unsigned long long*>(pv.base[pv.my] + 384) + phase;
-    if (atomicMax(sent, pv.epoch) < pv.epoch) {
-      if (stats_src != nullptr) {
-        for (int s = 0; s < pv.shards; ++s) {
-          unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.base[s] + 512) + 4 * pv.my;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned long long* hdr = reinterpret_cast<unsigned long long*>(pv.base[pv.my] + 384);
+    unsigned long long* sent = hdr + phase;          // epoch this rank has signalled
+    unsigned long long* seen = hdr + 4 + phase;      // epoch for which all peers' flags were already observed here
+    // later CTAs of the kernel (a grid is many waves) find `seen` set and skip the system-scope polling altogether
+    unsigned long long have = 0;
+    if (lane == 0) have = *reinterpret_cast<volatile unsigned long long*>(seen);
+    have = __shfl_sync(0xffffffffu, have, 0);
+    if (have < pv.epoch) {
+      bool first = false;
+      if (lane == 0) first = atomicMax(sent, pv.epoch) < pv.epoch;
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (first) {
+        if (stats_src != nullptr && lane < pv.shards) {
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.base[lane] + 512) + 4 * pv.my;
           for (int i = 0; i < 4; ++i) dst[i] = stats_src[i];
         }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < pv.shards)
+          st_release_sys(reinterpret_cast<unsigned long long*>(pv.base[lane] + 128 * phase) + pv.my, pv.epoch);
       }
-      __threadfence_system();
-      for (int s = 0; s < pv.shards; ++s)
-        st_release_sys(reinterpret_cast<unsigned long long*>(pv.base[s] + 128 * phase) + pv.my, pv.epoch);
-    }
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.base[pv.my] + 128 * phase);
-    const long long t0 = clock64();
-    for (int s = 0; s < pv.shards; ++s) {
-      while (ld_acquire_sys(mine + s) < pv.epoch) {
+      // lane s polls the flag of shard s: the S loads are in flight together
+      const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pv.base[pv.my] + 128 * phase);
+      const long long t0 = clock64();
+      bool ok = lane >= pv.shards;
+      while (!__all_sync(0xffffffffu, ok)) {
+        if (!ok) ok = ld_acquire_sys(mine + lane) >= pv.epoch;
         if (clock64() - t0 > 8000000000ll) {
-          printf("ieee_b200: rank %d waited in vain for shard %d (phase %d, epoch %llu)\n", pv.my, s, phase, pv.epoch);
+          if (!ok) printf("ieee_b200: rank %d waited in vain for shard %d (phase %d, epoch %llu)\n", pv.my, lane, phase, pv.epoch);
           __trap();
         }
       }
+      __threadfence();
+      if (lane == 0) atomicMax(seen, pv.epoch);
+    } else {
+      __threadfence();     // order this CTA's reads of the exchanged data after its read of `seen`
     }
-    __threadfence();
   }
   __syncthreads();
 }

@@ -160,6 +160,113 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   }
 }
 
+// Same arithmetic, one pass over HBM: the whole row lives in registers (NV float4 per lane, rows of up to NV * 128
+// floats), so the normalisation sums, the row maximum and the split all work on the loaded copy, and every lane has
+// NV independent 16-byte loads in flight.  fp32 rows with D % 4 == 0 and 16-byte alignment; identical results to
+// pack_rows_kernel (same per-lane element order in every reduction).
+template <int NV>
+__global__ void __launch_bounds__(256) pack_rows_reg_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
+                                                             int n_norm, int mode, const float* __restrict__ center,
+                                                             uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                             float* __restrict__ f32, float* __restrict__ norms,
+                                                             float* __restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ld;
+  const int nv = Dp / 128 + ((Dp % 128) ? 1 : 0);       // float4 slots per lane that touch the padded row
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nv && col < D) v[i] = __ldg(reinterpret_cast<const float4*>(xr + col));
+  }
+  float den[2] = {1.0f, 1.0f};
+  for (int pass = 0; pass < n_norm; ++pass) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nv) {
+        float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float u = t[j];
+          if (pass == 1) u = __fdiv_rn(u, den[0]);
+          s = __fmaf_rn(u, u, s);
+        }
+      }
+    }
+    s = warp_sum(s);
+    den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const int col = (i * 32 + lane) * 4;
+      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);      // (the centre is 9 KB: these loads hit L1)
+      if (center != nullptr && col < D) c4 = __ldg(reinterpret_cast<const float4*>(center + col));
+      const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n_norm >= 1) t[j] = __fdiv_rn(t[j], den[0]);
+        if (n_norm >= 2) t[j] = __fdiv_rn(t[j], den[1]);
+        t[j] = __fsub_rn(t[j], cc[j]);
+        amax = fmaxf(amax, fabsf(t[j]));
+      }
+      v[i] = make_float4(t[0], t[1], t[2], t[3]);       // the value the contraction multiplies (before scaling)
+    }
+  }
+  int e = 0;
+  if (mode == PACK_F16_HILO) {
+    amax = warp_max(amax);
+    if (amax > 0.f && amax < 3.0e38f) {
+      (void)frexpf(amax, &e);
+      e = max(-100, min(100, e)) - 14;
+    }
+  }
+  const float down = ldexpf(1.0f, -e);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    if (i < nv && col < Dp) {
+      const float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float u = t[j];
+        if (mode == PACK_BF16) {
+          const __nv_bfloat16 b = __float2bfloat16_rn(t[j]);
+          h[j] = __bfloat16_as_ushort(b);
+          l[j] = 0;
+          u = __bfloat162float(b);
+        } else if (mode == PACK_F16_HILO) {
+          const float y = t[j] * down;
+          const __half hh = __float2half_rn(y);
+          h[j] = __half_as_ushort(hh);
+          l[j] = __half_as_ushort(__float2half_rn(y - __half2float(hh)));
+        }
+        sq = __fmaf_rn(u, u, sq);
+      }
+      const int64_t o = row * (int64_t)Dp + col;
+      if (mode == PACK_F32) {
+        *reinterpret_cast<float4*>(f32 + o) = v[i];
+      } else {
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
+        if (mode == PACK_F16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) {
+    norms[row] = sq;
+    row_scale[row] = ldexpf(1.0f, e);
+  }
+}
+
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
                   const float* center, void* packed, cudaStream_t stream) {
   IEEE_REQUIRE(x != nullptr && packed != nullptr, "pack_features: null pointer");
@@ -188,7 +295,9 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
   if (dtype == IEEE_DTYPE_F32) {
     const float* xf = static_cast<const float*>(x);
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xf) & 15) == 0);
-    if (vec)
+    if (vec && L.Dp <= 24 * 128 && !(g_debug_flags & 64))
+      pack_rows_reg_kernel<24><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+    else if (vec)
       pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
     else
       pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
@@ -207,17 +316,16 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
 // the same for both operands of a contraction -- so a sample is enough, and for normalised features the mean of
 // the raw rows is simply scaled to unit length (m / max(|m|, 1e-12)) instead of normalising every sample row.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kCenterGroups = 32;
-
+// One launch: every CTA owns 128 columns, warp w adds sample rows w, w + 8, ...; the eight partial rows are summed
+// in a fixed order.  With `unit` a second, single-CTA launch scales the mean to unit length.
 template <typename T>
-__global__ void __launch_bounds__(256) center_partial_kernel(const T* __restrict__ x, int64_t ld, int64_t stride, int n_s, int D,
-                                                              float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) center_rows_kernel(const T* __restrict__ x, int64_t ld, int64_t stride, int n_s, int D,
+                                                           float* __restrict__ center) {
   __shared__ float red[8][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int g = blockIdx.y;
   const int col0 = blockIdx.x * 128 + lane * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = g + kCenterGroups * w; i < n_s; i += kCenterGroups * 8) {
+  for (int i = w; i < n_s; i += 8) {
     const T* xr = x + (int64_t)i * stride * ld;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -231,24 +339,15 @@ __global__ void __launch_bounds__(256) center_partial_kernel(const T* __restrict
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
     const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col < D) partial[(int64_t)g * D + col] = s;
+    if (col < D) center[col] = s * (1.0f / (float)n_s);
   }
 }
 
-__global__ void __launch_bounds__(1024) center_finish_kernel(const float* __restrict__ partial, int n_s, int D, int unit,
-                                                              float* __restrict__ center) {
+__global__ void __launch_bounds__(1024) center_unit_kernel(int D, float* __restrict__ center) {
   __shared__ float red[32];
   __shared__ float scale_s;
   float sq = 0.f;
-  const float inv = 1.0f / (float)n_s;
-  for (int col = threadIdx.x; col < D; col += 1024) {
-    float s = 0.f;
-    for (int g = 0; g < kCenterGroups; ++g) s += partial[(int64_t)g * D + col];
-    s *= inv;
-    center[col] = s;
-    sq = __fmaf_rn(s, s, sq);
-  }
-  if (!unit) return;
+  for (int col = threadIdx.x; col < D; col += 1024) sq = __fmaf_rn(center[col], center[col], sq);
   sq = warp_sum(sq);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
   __syncthreads();
@@ -261,25 +360,28 @@ __global__ void __launch_bounds__(1024) center_finish_kernel(const float* __rest
   for (int col = threadIdx.x; col < D; col += 1024) center[col] *= sc;
 }
 
-size_t feature_center_workspace_bytes(int64_t D) { return align256(size_t(kCenterGroups) * size_t(D) * 4); }
+size_t feature_center_workspace_bytes(int64_t D) { return 256; }   // (kept in the interface; the kernels need none)
 
 int feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
                    float* center, void* workspace, cudaStream_t stream) {
-  IEEE_REQUIRE(x && center && workspace, "feature_center: null pointer");
+  IEEE_REQUIRE(x && center, "feature_center: null pointer");
   IEEE_REQUIRE(rows > 0 && D > 0 && ld >= D && D <= (1 << 24), "feature_center: bad shape rows=%lld D=%lld ld=%lld",
                (long long)rows, (long long)D, (long long)ld);
   IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "feature_center: unknown dtype %d", dtype);
-  if (max_rows <= 0) max_rows = 512;
+  (void)workspace;
+  if (max_rows <= 0) max_rows = 64;
   const int n_s = (int)(rows < max_rows ? rows : max_rows);
   const int64_t stride = rows / n_s;
-  float* partial = static_cast<float*>(workspace);
-  dim3 grid((unsigned)((D + 127) / 128), kCenterGroups);
+  const unsigned grid = (unsigned)((D + 127) / 128);
   if (dtype == IEEE_DTYPE_F32)
-    center_partial_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, stride, n_s, (int)D, partial);
+    center_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, stride, n_s, (int)D, center);
   else
-    center_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, stride, n_s, (int)D, partial);
-  center_finish_kernel<<<1, 1024, 0, stream>>>(partial, n_s, (int)D, normalize ? 1 : 0, center);
-  count_launch(2);
+    center_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, stride, n_s, (int)D, center);
+  count_launch();
+  if (normalize) {
+    center_unit_kernel<<<1, 1024, 0, stream>>>((int)D, center);
+    count_launch();
+  }
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }

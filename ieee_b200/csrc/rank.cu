@@ -1149,6 +1149,117 @@ int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t sha
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// float64 distance matrices.  evaluate_py (rank.py:117, the function this fork runs) argsorts the matrix in the dtype
+// it arrives in, so two distances that differ below float32 resolution are ORDERED there, while a float32 copy would
+// tie them (and break the tie by index).  This path keeps the float64 order: one CTA per query, the relevant items'
+// (64-bit distance key, gallery index) thresholds sorted in shared memory, every row entry placed with a binary
+// search.  Not a roofline kernel -- the engine never produces float64 distances -- but the same counting form,
+// the same tie rule (NaN last, -0 == +0, equal distances by gallery index) and the same finalize stage.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t order_key64(double d) {
+  if (d != d) return ~uint64_t(0);
+  d += 0.0;
+  const uint64_t b = (uint64_t)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | (uint64_t(1) << 63));
+}
+__device__ __forceinline__ bool key96_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+constexpr int kF64Threads = 256;
+
+__global__ void __launch_bounds__(kF64Threads) rank_count_f64_kernel(
+    const double* __restrict__ distmat, int64_t ld, int64_t Q, int G, const int64_t* __restrict__ q_pids,
+    const int64_t* __restrict__ q_camids, const int64_t* __restrict__ g_camids, const long long* __restrict__ keys,
+    const int32_t* __restrict__ gcnt, const int32_t* __restrict__ goff, const int32_t* __restrict__ members, int64_t T, int cap,
+    int32_t* __restrict__ counts, unsigned long long* __restrict__ ties_out, int32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t fs_raw[];
+  uint64_t* Uk = reinterpret_cast<uint64_t*>(fs_raw);            // [cap] relevant, unsorted
+  uint64_t* Sk = Uk + cap;                                        // [cap] relevant, sorted
+  uint64_t* Jk = Sk + cap;                                        // [cap] junk
+  uint32_t* Ui = reinterpret_cast<uint32_t*>(Jk + cap);           // [cap]
+  uint32_t* Si = Ui + cap;
+  uint32_t* Ji = Si + cap;
+  int32_t* hist = reinterpret_cast<int32_t*>(Ji + cap);           // [cap + 2]
+  __shared__ int s_lo, s_n, s_nr, s_nj, s_ties;
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int stride = cap + 2;
+  int32_t* out = counts + q * stride;
+  if (tid == 0) {
+    const int s = group_find(keys, T, q_pids[q]);
+    s_lo = s >= 0 ? goff[s] : 0;
+    s_n = s >= 0 ? gcnt[s] : 0;
+    s_nr = 0; s_nj = 0; s_ties = 0;
+  }
+  __syncthreads();
+  const int n = s_n, lo = s_lo;
+  if (n > cap) {
+    if (tid == 0) { atomicMax(overflow, n); out[stride - 2] = 0; out[stride - 1] = 0; }
+    return;
+  }
+  const double* row = distmat + q * ld;
+  const long long cam = q_camids[q];
+  for (int t = tid; t < n; t += kF64Threads) {
+    const int gi = members[lo + t];
+    const uint64_t k = order_key64(row[gi]);
+    if (g_camids[gi] == cam) { const int p = atomicAdd(&s_nj, 1); Jk[p] = k; Ji[p] = (uint32_t)gi; }
+    else { const int p = atomicAdd(&s_nr, 1); Uk[p] = k; Ui[p] = (uint32_t)gi; }
+  }
+  __syncthreads();
+  const int R = s_nr, nj = s_nj;
+  if (tid == 0) { out[stride - 2] = R; out[stride - 1] = nj; }
+  if (R == 0) return;                                            // invalid query (rank.py:142-144)
+  for (int t = tid; t < R; t += kF64Threads) {                   // rank sort: (key, index) pairs are distinct
+    int pos = 0;
+    for (int j = 0; j < R; ++j) pos += key96_less(Uk[j], Ui[j], Uk[t], Ui[t]);
+    Sk[pos] = Uk[t];
+    Si[pos] = Ui[t];
+  }
+  for (int b = tid; b <= R; b += kF64Threads) hist[b] = 0;
+  __syncthreads();
+  auto place = [&](uint64_t k, uint32_t g, int delta) {
+    // lb = #{thresholds < (k, g)}; an entry is before threshold t iff t >= lb, or t >= lb + 1 when it IS threshold lb
+    int a = 0, e = R;
+    while (a < e) { const int m = (a + e) >> 1; if (key96_less(Sk[m], Si[m], k, g)) a = m + 1; else e = m; }
+    const bool is_thr = a < R && Sk[a] == k && Si[a] == g;
+    atomicAdd(&hist[a + (is_thr ? 1 : 0)], delta);
+    if (!is_thr) {                                               // bit-equal distance with a threshold: a tie pair
+      int same = 0;
+      for (int j = a; j < R && Sk[j] == k; ++j) ++same;
+      for (int j = a - 1; j >= 0 && Sk[j] == k; --j) ++same;
+      if (same) atomicAdd(&s_ties, delta * same);
+    }
+  };
+  for (int g = tid; g < G; g += kF64Threads) place(order_key64(row[g]), (uint32_t)g, 1);
+  __syncthreads();
+  for (int t = tid; t < nj; t += kF64Threads) place(Jk[t], Ji[t], -1);   // junk items were streamed too (rank.py:136-140)
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < R; ++k) { run += hist[k]; out[k] = run; }
+    if (ties_out != nullptr && s_ties != 0) atomicAdd(ties_out, (unsigned long long)(long long)s_ties);
+  }
+}
+
+int rank_count_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
+                   const int64_t* g_camids, const void* group, int32_t cap, int32_t* counts, unsigned long long* ties,
+                   int32_t* overflow, cudaStream_t stream) {
+  IEEE_REQUIRE(distmat && q_pids && q_camids && g_camids && group && counts && overflow, "rank_count_f64: null pointer");
+  IEEE_REQUIRE(Q >= 0 && G > 0 && G < (int64_t(1) << 31) && ld >= G && cap >= 1, "rank_count_f64: bad shape");
+  IEEE_REQUIRE(cap <= 4096, "rank_count_f64: %d same-identity gallery items per query exceed the float64 path's limit (4096)", cap);
+  if (Q == 0) return IEEE_OK;
+  GroupView v = group_view(group, G);
+  const size_t smem = size_t(cap) * (3 * 8 + 3 * 4) + size_t(cap + 2) * 4;
+  IEEE_ENSURE_DYN_SMEM(rank_count_f64_kernel, smem);
+  rank_count_f64_kernel<<<(unsigned)Q, kF64Threads, smem, stream>>>(distmat, ld, Q, (int)G, q_pids, q_camids, g_camids, v.keys, v.cnt,
+                                                                    v.off, v.members, v.T, cap, counts, ties, overflow);
+  count_launch();
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Junk-masked top-k (ranked list): threshold filter into a shared candidate buffer, compacted by bitonic sort.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTopkThreads = 256;

@@ -177,13 +177,47 @@ def evaluate_device(distmat: torch.Tensor, q_pids, g_pids, q_camids, g_camids, m
         return st.cmc, st.read_summary(), st
 
 
+# Limits of the kernels behind this module (include/ieee_b200.h); the reference has none of them, so they are checked
+# here with a message instead of surfacing as an error code from the library ("Limits").
+MAX_RANK_LIMIT = 8192          # rank_reduce_kernel's hit table
+TOPK_LIMIT = 1024              # ieee_topk's candidate buffer
+
+
+def check_limits(max_rank=None, k=None):
+    if max_rank is not None and max_rank > MAX_RANK_LIMIT:
+        raise ValueError("max_rank={} exceeds the {} ranks the CMC kernel tabulates".format(max_rank, MAX_RANK_LIMIT))
+    if k is not None and not 1 <= k <= TOPK_LIMIT:
+        raise ValueError("ranked lists hold between 1 and {} entries per query, got k={}".format(TOPK_LIMIT, k))
+
+
+def _evaluate_device_f64(d, q_pids, g_pids, q_camids, g_camids, max_rank):
+    dev = d.device
+    with torch.cuda.device(dev):
+        Q, G = d.shape
+        if d.stride(1) != 1:
+            d = d.contiguous()
+        lab = [_as_device(x, torch.int64, dev) for x in (q_pids, g_pids, q_camids, g_camids)]
+        lib = _lib.load()
+        cap_bound = int(min(G, 4096))
+        ws = torch.empty(lib.ieee_eval_workspace_bytes(Q, G, cap_bound), dtype=torch.uint8, device=dev)
+        k_eff = min(max_rank, G)
+        cmc = torch.empty(k_eff, dtype=torch.float32, device=dev)
+        summ = torch.empty(C.sizeof(_lib.EvalSummary), dtype=torch.uint8, device=dev)
+        _lib.call("ieee_eval_market1501_f64", d.data_ptr(), d.stride(0), Q, G, lab[0].data_ptr(), lab[1].data_ptr(),
+                  lab[2].data_ptr(), lab[3].data_ptr(), max_rank, cap_bound, cmc.data_ptr(), summ.data_ptr(), ws.data_ptr(),
+                  ws.numel(), _lib.stream())
+        summary = _lib.EvalSummary.from_buffer_copy(summ.cpu().numpy().tobytes())
+    return cmc, summary
+
+
 def eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank):
     """Evaluation with market1501 metric (reference: rank.py:103-171).
     Key: for each query identity, its gallery images from the same camera view are discarded."""
     _lib.require_cuda()
     dev = distmat.device if isinstance(distmat, torch.Tensor) and distmat.is_cuda else torch.device(
         "cuda", torch.cuda.current_device())
-    d = _as_device(distmat, torch.float32, dev)
+    is_f64 = (distmat.dtype == torch.float64) if isinstance(distmat, torch.Tensor) else (np.asarray(distmat).dtype == np.float64)
+    d = _as_device(distmat, torch.float64 if is_f64 else torch.float32, dev)
     assert d.dim() == 2
     num_q, num_g = d.shape
     if num_g < max_rank:
@@ -191,17 +225,87 @@ def eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank):
         print("Note: number of gallery samples is quite small, got {}".format(num_g))
     if num_q == 0 or num_g == 0:      # no query can have a kept match: the reference ends in its assertion (rank.py:165)
         raise AssertionError("Error: all query identities do not appear in gallery")
+    check_limits(max_rank=max_rank)
+    if is_f64:
+        # rank.py:117 argsorts the matrix in the dtype it is given: float64 distances keep their float64 order
+        cmc, summary = _evaluate_device_f64(d, q_pids, g_pids, q_camids, g_camids, max_rank)
+        raise_for_status(summary, max_rank)
+        return cmc.cpu().numpy(), float(summary.mAP)
     cmc, summary, _ = evaluate_device(d, q_pids, g_pids, q_camids, g_camids, max_rank)
     raise_for_status(summary, max_rank)
     return cmc.cpu().numpy(), float(summary.mAP)
 
 
+# The fork's own evaluate_rank(use_metric_cuhk03=True) dies with a TypeError (rank.py:236-239 hands 6 arguments to the
+# 8-argument eval_cuhk03): that stays the default, so a drop-in behaves like the reference.  Set this flag (or call
+# eval_cuhk03 directly) to get the protocol upstream torchreid and rank_cy.pyx implement.
+ENABLE_CUHK03 = False
+CUHK03_MAX_GALLERY = 1024      # the junk-masked ranked list comes from ieee_topk (k <= 1024)
+
+
+def eval_cuhk03(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, q_timeids=None, g_timeids=None, num_repeats=10):
+    """Evaluation with the cuhk03 metric (single-gallery-shot; reference: rank.py:24-100, rank_cy.pyx:37-153).
+    Key: one image for each gallery identity is randomly sampled for each query identity, `num_repeats` (10) times.
+
+    The ranking runs on the GPU: one junk-masked ranked list per query (``ieee_topk`` with k = G; the junk rule is
+    same pid AND same camera, AND same time id when the fork's two extra arrays are given, rank.py:48).  The sampling
+    is the reference's own: NumPy's global generator, one ``np.random.choice`` per gallery identity in order of first
+    appearance in the kept ranked list (rank.py:66-72) -- seed NumPy and the result is the reference's for that seed
+    (ties in the distances are ranked by gallery index; the reference leaves them to an unstable argsort)."""
+    _lib.require_cuda()
+    q_pids, g_pids, q_camids, g_camids = (np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a).astype(np.int64)
+                                          for a in (q_pids, g_pids, q_camids, g_camids))
+    num_q, num_g = distmat.shape
+    if num_g < max_rank:
+        max_rank = num_g
+        print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    if num_q == 0 or num_g == 0:
+        raise AssertionError("Error: all query identities do not appear in gallery")
+    if num_g > CUHK03_MAX_GALLERY:
+        raise ValueError("eval_cuhk03: the ranked lists come from the top-k kernel, which holds at most {} gallery items per "
+                         "query (got {}); the protocol is meant for CUHK03-sized galleries".format(CUHK03_MAX_GALLERY, num_g))
+    qc, gc = q_camids, g_camids
+    if q_timeids is not None:     # same camera AND same time id <=> same (camera, time) pair: one composite id
+        qt, gt = np.asarray(q_timeids).astype(np.int64), np.asarray(g_timeids).astype(np.int64)
+        lo = min(qt.min(), gt.min())
+        span = int(max(qt.max(), gt.max()) - lo) + 1
+        qc, gc = q_camids * span + (qt - lo), g_camids * span + (gt - lo)
+    ranked = topk_ranked_list(distmat, q_pids, g_pids, qc, gc, k=num_g)[0].cpu().numpy()
+    rows, aps = [], []
+    for q in range(num_q):
+        kept = ranked[q][ranked[q] >= 0]
+        kept_pids = g_pids[kept]
+        hits = (kept_pids == q_pids[q]).astype(np.int32)
+        if not hits.any():
+            continue                                              # query identity does not appear in the gallery
+        first_seen = {}
+        for pos, pid in enumerate(kept_pids.tolist()):
+            first_seen.setdefault(pid, []).append(pos)
+        acc = np.zeros(max_rank, dtype=np.float32)
+        for _ in range(num_repeats):
+            shown = np.zeros(hits.size, dtype=bool)
+            for positions in first_seen.values():                 # one gallery image per person
+                shown[np.random.choice(positions)] = True
+            curve = np.minimum(np.cumsum(hits[shown]), 1)[:max_rank].astype(np.float32)
+            acc[: curve.size] += curve
+        rows.append(acc / num_repeats)
+        precision = np.cumsum(hits) / (np.arange(hits.size) + 1.0)
+        aps.append(float((precision * hits).sum() / hits.sum()))
+    if not rows:
+        raise AssertionError("Error: all query identities do not appear in gallery")
+    cmc = np.asarray(rows).astype(np.float32).sum(0) / float(len(rows))
+    return cmc.astype(np.float32), float(np.mean(aps))
+
+
 def evaluate_py(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, use_metric_cuhk03):
     if use_metric_cuhk03:
+        if ENABLE_CUHK03:
+            return eval_cuhk03(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
         # rank.py:236-239 passes 6 arguments to the 8-argument eval_cuhk03, so the reference raises
-        # TypeError on this branch; the single-gallery-shot protocol is out of scope.
+        # TypeError on this branch; the drop-in does the same unless ENABLE_CUHK03 is set.
         raise TypeError("eval_cuhk03() missing 2 required positional arguments: 'g_camids' and 'max_rank' "
-                        "(the reference's cuhk03 branch is unreachable; only the Market-1501 protocol is provided)")
+                        "(the reference's cuhk03 branch is unreachable; set ieee_b200.metrics.rank.ENABLE_CUHK03 = True "
+                        "or call eval_cuhk03 for the single-gallery-shot protocol)")
     return eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
 
 
@@ -226,6 +330,7 @@ def topk_ranked_list(distmat, q_pids=None, g_pids=None, q_camids=None, g_camids=
     _lib.require_cuda()
     dev = distmat.device if isinstance(distmat, torch.Tensor) and distmat.is_cuda else torch.device(
         "cuda", torch.cuda.current_device())
+    check_limits(k=k)
     d = _as_device(distmat, torch.float32, dev)
     Q, G = d.shape
     idx = torch.empty((Q, k), dtype=torch.int32, device=dev)

@@ -107,7 +107,7 @@ size_t ieee_packed_bytes(int64_t rows, int64_t D, int precision);
  * same centre. */
 int ieee_pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize,
                        int precision, const float* center, void* packed, ieee_stream_t stream);
-/* Centre for ieee_pack_features: column mean over up to max_rows (0: 512) evenly strided rows of x, scaled to unit
+/* Centre for ieee_pack_features: column mean over up to max_rows (0: 64) evenly strided rows of x, scaled to unit
  * length when `normalize` is set (the rows will be).  Deterministic (fixed summation order).  center: float32[D];
  * workspace: ieee_feature_center_workspace_bytes(D). */
 size_t ieee_feature_center_workspace_bytes(int64_t D);
@@ -241,6 +241,15 @@ size_t ieee_gallery_prepare_workspace_bytes(int64_t D);
 int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int64_t D, int metric, int normalize,
                          int precision, const int64_t* g_pids, const void* center_src, int64_t ld_src, int64_t rows_src,
                          float* center, void* g_packed, void* group, void* workspace, ieee_stream_t stream);
+
+/* The same for a FLOAT64 distance matrix, ranked in float64 order: evaluate_py (rank.py:117, the function this fork
+ * runs) argsorts the matrix in the dtype it is given, so distances that differ below float32 resolution are ordered
+ * there and must not be tied by a float32 copy.  Same workspace as ieee_eval_market1501; at most 4096 same-identity
+ * gallery items per query. */
+int ieee_eval_market1501_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids,
+                             const int64_t* g_pids, const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank,
+                             int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace,
+                             size_t workspace_bytes, ieee_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Retrieval + evaluation in ONE call: the tail of Engine._evaluate (engine.py:391-417) --

@@ -120,6 +120,52 @@ def evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=20, use_
     return eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, stable=stable)
 
 
+def eval_cuhk03(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, q_timeids=None, g_timeids=None,
+                num_repeats: int = 10, stable: bool = True):
+    """Single-gallery-shot protocol: rank.py:24-100 (this fork: 8 arguments, time ids join the junk rule, :48) and
+    rank_cy.pyx:37-153 (the upstream 6-argument form, the one that still runs: rank.py's uses np.bool, gone from NumPy).
+
+    Per query: rank; drop gallery items with the query's pid AND camera (AND time id when given); skip the query when
+    nothing relevant is left; then `num_repeats` times keep ONE random item per gallery identity -- identities visited in
+    order of first appearance in the kept ranked list, one ``np.random.choice(positions)`` each (rank.py:66-72) -- and
+    accumulate the clipped cumulative hit vector of that sample; AP comes from the unsampled kept list (:81-86).
+    RNG parity = NumPy's global generator consumed in exactly that order: seed it, call, compare.
+    Returns (cmc float32[K'], mAP float64)."""
+    distmat = np.asarray(distmat)
+    q_pids, g_pids, q_camids, g_camids = (np.asarray(a) for a in (q_pids, g_pids, q_camids, g_camids))
+    num_q, num_g = distmat.shape
+    if num_g < max_rank:
+        max_rank = num_g
+        print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    order = _argsort_rows(distmat, stable)
+    rows, aps = [], []
+    for q in range(num_q):
+        o = order[q]
+        junk = (g_pids[o] == q_pids[q]) & (g_camids[o] == q_camids[q])
+        if q_timeids is not None:
+            junk &= np.asarray(g_timeids)[o] == np.asarray(q_timeids)[q]
+        hits = (g_pids[o] == q_pids[q])[~junk].astype(np.int32)
+        if not hits.any():
+            continue
+        kept_pids = g_pids[o][~junk]
+        groups = {}
+        for pos, pid in enumerate(kept_pids.tolist()):
+            groups.setdefault(pid, []).append(pos)
+        acc = np.zeros(max_rank, dtype=np.float32)
+        for _ in range(num_repeats):
+            pick = np.zeros(hits.size, dtype=bool)
+            for positions in groups.values():
+                pick[np.random.choice(positions)] = True
+            run = np.minimum(hits[pick].cumsum(), 1)[:max_rank].astype(np.float32)
+            acc[: run.size] += run                               # (fewer identities than max_rank: rank.py would fail to add)
+        rows.append(acc / num_repeats)
+        run = hits.cumsum()
+        aps.append(float((run / (np.arange(hits.size) + 1.0) * hits).sum() / hits.sum()))
+    assert len(rows) > 0, "Error: all query identities do not appear in gallery"
+    cmc = np.asarray(rows).astype(np.float32).sum(0) / float(len(rows))
+    return cmc.astype(np.float32), float(np.mean(aps))
+
+
 def kept_positions(distmat, q_pids, g_pids, q_camids, g_camids):
     """Sort-free form of rank.py:136-160, used to check kernel intermediates.
 

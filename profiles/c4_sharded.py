@@ -71,9 +71,12 @@ def barrier():
     torch.cuda.synchronize()
 
 
+last = {}
+
+
 def step():
-    ev = RetrievalEvaluator(gf, g_pids_all[g0:g1], g_cams_all[g0:g1], "euclidean", False, args.precision, 20, group=group,
-                            g_offset=g0, g_total=args.gallery)
+    ev = last["ev"] = RetrievalEvaluator(gf, g_pids_all[g0:g1], g_cams_all[g0:g1], "euclidean", False, args.precision, 20,
+                                         group=group, g_offset=g0, g_total=args.gallery)
     return ev.evaluate(qf, q_pids, q_cams)
 
 
@@ -92,7 +95,8 @@ cmc, mAP, info = out
 line = {"workload": f"C4 Q={args.queries} G={args.gallery} D={args.dim} {args.precision} euclidean", "n_gpus": world,
         "ms_per_step": float(ms.item()), "queries_per_s": args.queries / float(ms.item()) * 1e3,
         "distance_tflops_algorithmic_per_gpu": 2.0 * args.queries * (g1 - g0) * args.dim / float(ms.item()) / 1e9,
-        "mAP": mAP, "rank1": float(cmc[0]), "num_valid": int(info["num_valid"]), "num_ties": int(info["num_ties"]), "cap": info["cap"]}
+        "mAP": mAP, "rank1": float(cmc[0]), "num_valid": int(info["num_valid"]), "num_ties": int(info["num_ties"]), "cap": info["cap"],
+        "exchange": last["ev"].exchange}
 
 if args.check > 0:
     n = min(args.check, args.queries)
@@ -104,7 +108,8 @@ if args.check > 0:
         del parts
     else:
         gf_all = gf
-    single = RetrievalEvaluator(gf_all, g_pids_all, g_cams_all, "euclidean", False, args.precision, 20)
+    # same centre as the sharded run (it is taken from the query set: here a different one, the first n queries)
+    single = RetrievalEvaluator(gf_all, g_pids_all, g_cams_all, "euclidean", False, args.precision, 20, center=last["ev"].center)
     _, _, info1 = single.evaluate(qf[:n], q_pids[:n], q_cams[:n])
     same_first = bool(torch.equal(info1["first"], info["first"][:n]))
     same_ap = bool(torch.equal(info1["ap"], info["ap"][:n]))

@@ -264,3 +264,95 @@ def test_market1501_shape_full_size():
     cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
     cmc, mAP = evaluate_rank(d_dev, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
     assert np.array_equal(cmc, cmc_o) and abs(mAP - map_o) < 1e-9 and 0.05 < mAP < 0.95
+
+
+def test_cuhk03_protocol_matches_reference_for_fixed_seeds(golden_dir):
+    """Single-gallery-shot protocol (rank.py:24-100, rank_cy.pyx:37-153): ranked lists from the GPU, sampling with
+    NumPy's generator in the reference's call order -- equal to the golden file the compiled reference wrote, per seed."""
+    from ieee_b200.metrics import rank as M
+    g = np.load(os.path.join(golden_dir, "cuhk03_small.npz"))
+    args = (g["distmat"], g["q_pids"], g["g_pids"], g["q_camids"], g["g_camids"])
+    for seed in (0, 1234):
+        for k in (5, 20):
+            np.random.seed(seed)
+            cmc, mAP = M.eval_cuhk03(*args, k)
+            np.random.seed(seed)
+            cmc_o, map_o = R.eval_cuhk03(*args, k)
+            assert np.array_equal(cmc, cmc_o) and mAP == map_o                  # the oracle restatement, bit for bit
+            np.testing.assert_allclose(cmc, g[f"cmc_s{seed}_k{k}"], rtol=0, atol=2e-7)   # rank_cy accumulates in float32
+            assert abs(mAP - float(g[f"mAP_s{seed}_k{k}"])) < 1e-7
+    # the fork's time ids (rank.py:48): one shared time id changes nothing; per-item time ids un-junk every pair
+    np.random.seed(5)
+    a = M.eval_cuhk03(*args, 20, q_timeids=np.zeros(60, int), g_timeids=np.zeros(400, int))
+    np.random.seed(5)
+    b = M.eval_cuhk03(*args, 20)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    np.random.seed(5)
+    c = M.eval_cuhk03(*args, 20, q_timeids=np.arange(60), g_timeids=1000 + np.arange(400))
+    np.random.seed(5)
+    c_o = R.eval_cuhk03(*args, 20, q_timeids=np.arange(60), g_timeids=1000 + np.arange(400))
+    assert np.array_equal(c[0], c_o[0]) and c[1] == c_o[1]
+    # drop-in default: the fork's branch raises TypeError (rank.py:236-239); the protocol is an explicit opt-in
+    with pytest.raises(TypeError):
+        evaluate_rank(*args, max_rank=20, use_metric_cuhk03=True)
+    M.ENABLE_CUHK03 = True
+    try:
+        np.random.seed(0)
+        cmc, mAP = evaluate_rank(*args, max_rank=20, use_metric_cuhk03=True)
+        np.testing.assert_allclose(cmc, g["cmc_s0_k20"], rtol=0, atol=2e-7)
+    finally:
+        M.ENABLE_CUHK03 = False
+    with pytest.raises(ValueError):
+        M.eval_cuhk03(np.zeros((2, 2000), np.float32), np.zeros(2, int), np.zeros(2000, int), np.zeros(2, int), np.ones(2000, int), 5)
+
+
+def test_float64_distmat_is_ranked_in_float64_order():
+    """evaluate_py (rank.py:117) argsorts the matrix in the dtype it arrives in.  Distances that only differ below
+    float32 resolution are ordered there; a float32 copy ties them and the index rule can pick the other order."""
+    rng = np.random.RandomState(3)
+    Q, G = 40, 600
+    d = rng.uniform(1.0, 2.0, size=(Q, G))
+    q_pids, g_pids = rng.randint(0, 15, Q), rng.randint(0, 15, G)
+    q_cams, g_cams = rng.randint(0, 3, Q), rng.randint(0, 3, G)
+    # for every query: a relevant item and an irrelevant one at a LOWER index, equal in float32, relevant one closer in float64
+    flips = 0
+    for q in range(Q):
+        rel = np.nonzero((g_pids == q_pids[q]) & (g_cams != q_cams[q]))[0]
+        irr = np.nonzero(g_pids != q_pids[q])[0]
+        if rel.size == 0 or irr.size == 0 or irr[0] > rel[-1]:
+            continue
+        r, w = rel[-1], irr[0]                                # w < r
+        base = np.float64(np.float32(1.0 + 1e-3 * q))
+        d[q, r], d[q, w] = base, base + 2e-9                  # equal after rounding to float32
+        assert np.float32(d[q, r]) == np.float32(d[q, w]) and d[q, r] < d[q, w]
+        flips += 1
+    assert flips > 20
+    cmc, mAP = evaluate_rank(d, q_pids, g_pids, q_cams, g_cams, max_rank=20)
+    cmc_o, map_o = R.evaluate_rank(d, q_pids, g_pids, q_cams, g_cams, max_rank=20)       # float64 argsort, no ties
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - map_o) < 1e-12
+    if ref.available():
+        cmc_r, map_r = ref.evaluate_rank(d, q_pids, g_pids, q_cams, g_cams, max_rank=20)  # the reference's own evaluate_py
+        assert np.array_equal(cmc, cmc_r) and abs(mAP - map_r) < 1e-12
+    # the float32 copy really is a different problem: index order puts the irrelevant item first
+    cmc32, map32 = evaluate_rank(d.astype(np.float32), q_pids, g_pids, q_cams, g_cams, max_rank=20)
+    assert map32 < mAP
+    # torch float64 tensors on the device take the same path
+    cmc_t, map_t = evaluate_rank(torch.from_numpy(d).cuda(), q_pids, g_pids, q_cams, g_cams, max_rank=20)
+    assert np.array_equal(cmc_t, cmc) and map_t == mAP
+    # NaN last, -0 == +0, ties by index: same conventions as the float32 kernels
+    d2 = np.round(rng.uniform(0, 8, size=(Q, G)))
+    d2[:, ::17] = np.nan
+    d2[:, 5] = -0.0
+    cmc2, map2 = evaluate_rank(d2, q_pids, g_pids, q_cams, g_cams, max_rank=20)
+    cmc2_o, map2_o = R.evaluate_rank(d2, q_pids, g_pids, q_cams, g_cams, max_rank=20)
+    assert np.array_equal(cmc2, cmc2_o) and abs(map2 - map2_o) < 1e-12
+
+
+def test_limits_are_reported_in_python():
+    d = np.zeros((3, 10), np.float32)
+    lab = (np.zeros(3, int), np.zeros(10, int), np.zeros(3, int), np.ones(10, int))
+    with pytest.raises(ValueError, match="ranked lists hold"):
+        topk_ranked_list(d, *lab, k=5000)
+    big = np.zeros((2, 9000), np.float32)
+    with pytest.raises(ValueError, match="max_rank"):
+        evaluate_rank(big, np.zeros(2, int), np.zeros(9000, int), np.zeros(2, int), np.ones(9000, int), max_rank=9000)
