@@ -65,64 +65,44 @@ def bench_config(n_gpus: int) -> dict:
 
 
 class ClockSampler:
-    """SM clock / throttle reasons while the timed region runs, sampled by an `nvidia-smi -lms` child process (the
-    profiling recipe's clocks line): a sampling THREAD in this process would take the GIL from the loop being timed --
-    and with several ranks every rank waits for the slowest host.  Falls back to one NVML reading when nvidia-smi is
-    not on the PATH."""
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region, read through NVML by the timing loop itself at a few
+    points between steps (rank 0 only; ~0.1 ms per reading, inside the timed region).  Neither a sampling thread (it
+    competes for the GIL with the loop being timed, and with several ranks everybody waits for the slowest host) nor an
+    `nvidia-smi -lms` child process (its polling slowed a 2-GPU step from 0.9 to 3.4 ms) leaves the step alone."""
 
-    def __init__(self, index: int, period_ms: int = 5, enabled: bool = True):
-        self.index, self.proc = index, None
+    def __init__(self, index: int, enabled: bool = True):
+        self.samples, self.reasons, self.max_mhz, self.nv = [], set(), None, None
         if not enabled:
             return
-        import shutil
-        import subprocess
-        exe = shutil.which("nvidia-smi")
-        if exe:
-            try:
-                self.proc = subprocess.Popen([exe, "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                              "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            except Exception:
-                self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.names = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                          "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                          "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                          "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        except Exception:
+            self.nv = None
 
-    def start(self):
-        if self.proc is not None:
-            time.sleep(0.05)                      # let the child take its first readings before the region starts
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in self.names.items():
+                if mask & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
 
-    def stop(self):
-        samples, reasons, max_mhz = [], set(), None
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                out, _ = self.proc.communicate(timeout=5)
-            except Exception:
-                self.proc.kill()
-                out = ""
-            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-            for ln in out.splitlines():
-                parts = [x.strip() for x in ln.split(",")]
-                if len(parts) < 6:
-                    continue
-                try:
-                    samples.append(float(parts[0]))
-                    max_mhz = float(parts[1])
-                except ValueError:
-                    continue
-                for name, val in zip(names, parts[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        else:
-            try:
-                import pynvml
-                pynvml.nvmlInit()
-                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-                samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            except Exception:
-                pass
-        return {"sm_mhz": statistics.median(samples) if samples else None, "sm_max_mhz": max_mhz,
-                "reasons": sorted(reasons), "samples": len(samples), "how": "nvidia-smi -lms child process" if self.proc else "nvml, one reading"}
+    def result(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "how": "NVML readings taken by the timing loop between steps of the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -465,15 +445,17 @@ def run_ours(args):
             fn()
         barrier()
         sampler = ClockSampler(local_rank, enabled=rank == 0)      # rank 0 samples; the others stay quiet
-        sampler.start()
+        at = {steps // 4, steps // 2, (3 * steps) // 4}
         l0 = lib.ieee_launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        for _ in range(steps):
+        for i in range(steps):
             out = fn()
+            if i in at:
+                sampler.sample()
         stop.record()
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.result()
         ms = start.elapsed_time(stop)
         launches = lib.ieee_launch_count() - l0
         if world > 1:

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libieee_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_VALID_QUERY, ERR_SHORT_RANK_LIST, ERR_CAPACITY = range(7)
 METRICS = {"euclidean": 0, "cosine": 1}
+INTERNAL_METRICS = {"neg_dot": 2}          # -(a . b): GNN re-ranking (not a torchreid metric name)
 PRECISIONS = {"f16x3": 0, "bf16": 1, "fp32_simt": 2}
 DTYPES = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -71,6 +72,8 @@ SIGNATURES = {
     "ieee_set_fused_chunk": (C.c_int, [C.c_int]),
     "ieee_topk": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
     "ieee_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
+    "ieee_gnn_rerank_workspace_bytes": (sz, [i64, i32]),
+    "ieee_gnn_rerank": (C.c_int, [vp, i64, i64, i32, i32, vp, i64, vp, sz, vp]),
     "ieee_rerank_workspace_bytes": (sz, [i64, i64, i32, i32]),
     "ieee_rerank": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, C.c_double, vp, i64, vp, sz, vp]),
 }

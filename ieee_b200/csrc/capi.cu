@@ -90,6 +90,10 @@ int fused_eval(const void* q_packed, int64_t Q, const void* g_packed, const void
                ieee_eval_summary* summary, double* per_query_ap, int32_t* per_query_first, unsigned long long* stats_out,
                void* workspace, size_t workspace_bytes, cudaStream_t stream, int cta_group);
 
+size_t gnn_rerank_workspace_bytes(int64_t N, int32_t k1);
+int gnn_rerank(const float* neg_score, int64_t lds, int64_t N, int32_t k1, int32_t k2, float* A, int64_t ldA, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream);
+
 static int g_cta_group = -1;   // IEEE_B200_CTA_GROUP=1|2 overrides the default (2) pairing of the tensor-core kernel
 static int cta_group_default() {
   if (g_cta_group < 0) {
@@ -231,7 +235,7 @@ int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, i
   IEEE_REQUIRE(Q >= 0 && G >= 0 && D > 0 && ldo >= G, "distmat: bad shape Q=%lld G=%lld D=%lld ldo=%lld", (long long)Q,
                (long long)G, (long long)D, (long long)ldo);
   IEEE_REQUIRE(Q < (int64_t(1) << 31) && G < (int64_t(1) << 31), "distmat: Q and G must fit int32");
-  IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
+  IEEE_REQUIRE(metric >= IEEE_METRIC_EUCLIDEAN && metric <= IEEE_METRIC_NEG_DOT, "unknown metric %d", metric);
   if (Q == 0 || G == 0) return IEEE_OK;
   if (precision == IEEE_PREC_FP32_SIMT) return distmat_simt(q_packed, Q, g_packed, G, D, metric, out, ldo, (cudaStream_t)stream);
   IEEE_REQUIRE(precision == IEEE_PREC_F16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
@@ -598,6 +602,15 @@ int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq
   if (rc) return rc;
   return rerank(q_g, ld_qg, q_q, ld_qq, g_g, ld_gg, Q, G, k1, k2, lambda_value, out, ldo, workspace, workspace_bytes,
                 (cudaStream_t)stream);
+}
+
+size_t ieee_gnn_rerank_workspace_bytes(int64_t N, int32_t k1) { return gnn_rerank_workspace_bytes(N, k1); }
+
+int ieee_gnn_rerank(const float* neg_score, int64_t lds, int64_t N, int32_t k1, int32_t k2, float* A, int64_t ldA,
+                    void* workspace, size_t workspace_bytes, ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return gnn_rerank(neg_score, lds, N, k1, k2, A, ldA, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ---- retrieval + evaluation with the count fused into the contraction ----------------------------------------------

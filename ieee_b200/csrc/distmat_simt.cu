@@ -10,8 +10,8 @@ constexpr int SK = 16;   // k slab
 
 __global__ void __launch_bounds__(256) distmat_simt_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                             const float* __restrict__ rq, const float* __restrict__ rg,
-                                                            float alpha, int Q, int G, int Dp, float* __restrict__ out,
-                                                            int64_t ldo) {
+                                                            float alpha, float base0, int Q, int G, int Dp,
+                                                            float* __restrict__ out, int64_t ldo) {
   __shared__ float sa[SK][ST + 1];
   __shared__ float sb[SK][ST + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) distmat_simt_kernel(const float* __restri
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
     if (row >= Q) continue;
-    const float r1 = rq ? rq[row] : 1.0f;
+    const float r1 = rq ? rq[row] : base0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tx * 4 + j;
@@ -61,7 +61,8 @@ int distmat_simt(const void* q_packed, int64_t Q, const void* g_packed, int64_t 
   distmat_simt_kernel<<<grid, 256, 0, stream>>>(
       reinterpret_cast<const float*>(qb), reinterpret_cast<const float*>(gb),
       euclid ? reinterpret_cast<const float*>(qb + lq.norm_off) : nullptr,
-      euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr, euclid ? -2.0f : -1.0f, (int)Q, (int)G,
+      euclid ? reinterpret_cast<const float*>(gb + lg.norm_off) : nullptr, euclid ? -2.0f : -1.0f,
+      metric == IEEE_METRIC_NEG_DOT ? 0.0f : 1.0f, (int)Q, (int)G,
       (int)lq.Dp, out, ldo); count_launch();
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;

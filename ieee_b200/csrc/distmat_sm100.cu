@@ -59,7 +59,8 @@ struct GemmParams {
   int Q, G;
   int num_kb;        // Dp / 64
   int nseg;          // 1 (BF16) or 3 (F16X3)
-  float alpha;       // -2 (euclidean) or -1 (cosine)
+  float alpha;       // -2 (euclidean) or -1 (cosine, negative dot product)
+  float base0;       // additive term when there are no row terms: 1 (cosine: 1 - a.b) or 0 (negative dot product)
   int num_m_tiles, num_n_tiles;
   int panel_m;       // m tiles per raster panel: the panel's A rows stay L2-resident while it sweeps all n tiles
   uint32_t idesc;    // tcgen05 instruction descriptor (operand format, M, N)
@@ -225,7 +226,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int col_tile = n_blk * BLOCK_N;
       // this thread's row terms (thread <-> TMEM lane <-> output row)
       const int my_row = row0 + lane;
-      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : 1.0f;
+      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : p.base0;
       const float coef_row = p.alpha * ((p.sq != nullptr && my_row < p.Q) ? p.sq[my_row] : 1.0f);
       // the tile's column terms, one private copy per warp (no cross-warp barrier needed)
       __syncwarp();
@@ -483,7 +484,7 @@ distmat_umma_chunked_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const _
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int col0 = n_blk * BLOCK_N + half * 128;
       const int my_row = row0 + lane;
-      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : 1.0f;
+      const float rq_row = (p.rq != nullptr) ? (my_row < p.Q ? p.rq[my_row] : 0.0f) : p.base0;
       const float coef_row = p.alpha * ((p.sq != nullptr && my_row < p.Q) ? p.sq[my_row] : 1.0f);
       __syncwarp();
 #pragma unroll
@@ -818,6 +819,7 @@ static int gemm_setup(GemmLaunch& L, const void* q_packed, int64_t Q, const void
   p.sq = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(qb + lq.scale_off) : nullptr;
   p.sg = precision == IEEE_PREC_F16X3 ? reinterpret_cast<const float*>(gb + lg.scale_off) : nullptr;
   p.alpha = euclid ? -2.0f : -1.0f;
+  p.base0 = metric == IEEE_METRIC_NEG_DOT ? 0.0f : 1.0f;
   p.out = out;
   p.ldo = ldo;
   p.Q = (int)Q;

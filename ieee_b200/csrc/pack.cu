@@ -274,7 +274,7 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
                (long long)D, (long long)ld);
   IEEE_REQUIRE(D <= (1 << 24), "pack_features: feature dim too large");
   IEEE_REQUIRE(dtype == IEEE_DTYPE_F32 || dtype == IEEE_DTYPE_BF16, "pack_features: unknown dtype %d", dtype);
-  IEEE_REQUIRE(metric == IEEE_METRIC_EUCLIDEAN || metric == IEEE_METRIC_COSINE, "unknown metric %d", metric);
+  IEEE_REQUIRE(metric >= IEEE_METRIC_EUCLIDEAN && metric <= IEEE_METRIC_NEG_DOT, "unknown metric %d", metric);
   IEEE_REQUIRE(precision >= IEEE_PREC_F16X3 && precision <= IEEE_PREC_FP32_SIMT, "unknown precision %d", precision);
   IEEE_REQUIRE(center == nullptr || metric == IEEE_METRIC_EUCLIDEAN,
                "pack_features: a centre only applies to the euclidean metric (cosine is not translation invariant)");

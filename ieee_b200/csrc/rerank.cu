@@ -484,4 +484,123 @@ int rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, con
   return IEEE_OK;
 }
 
+// =========================================================================================================
+// GNN re-ranking (torchreid/utils/GPU-Re-Ranking/gnn_reranking.py:27-59 and its two CUDA extensions), as an alternative
+// `rerank` mode.  Input: the negated similarity matrix -(X_u X_u^T) over queries + gallery (our contraction with the
+// NEG_DOT metric).  Steps, all on N x N float32 matrices (N = Q + G; 1.5 GB at Market scale, nothing on a 180 GB part):
+//   top-k1 neighbours per row (ieee_topk on the negated scores: largest similarity first, ties by index)  :36-38
+//   A[i, rank[i, j]] = 1                              build_adjacency_matrix_kernel.cu:10-17
+//   S = S * S                                          :42
+//   twice, if k2 != 1:  A = A + A^T;  A[i, :] = sum_{j < k2} S[i, j] * A[rank[i, j], :];  A[i, :] /= |A[i, :]|_2
+//                                                      :46-53, gnn_propagate_kernel.cu:8-22
+// The caller finishes with cosine = A[:Q] A[Q:]^T (:55) -- again our contraction.
+// =========================================================================================================
+__global__ void gnn_square_kernel(const float* __restrict__ val, float* __restrict__ S, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) S[i] = val[i] * val[i];                 // (-s)^2 == s^2: the negation of the scores drops out here
+}
+
+__global__ void gnn_adjacency_kernel(const int32_t* __restrict__ rank, int k1, int64_t N, float* __restrict__ A, int64_t ld) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * k1) return;
+  const int64_t i = e / k1;
+  const int32_t j = rank[e];
+  if (j >= 0) A[i * ld + j] = 1.0f;
+}
+
+__global__ void __launch_bounds__(256) gnn_symmetrise_kernel(const float* __restrict__ A, float* __restrict__ B, int64_t N, int64_t ld) {
+  __shared__ float t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t row = bx + r, col = by + tx;             // the transposed tile
+    t[r][tx] = (row < N && col < N) ? A[row * ld + col] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t row = by + r, col = bx + tx;
+    if (row < N && col < N) B[row * ld + col] = A[row * ld + col] + t[tx][r];
+  }
+}
+
+// out[i, f] = sum_{j < k2} S[i, j] * A[rank[i, j], f], summed in j order like the reference kernel
+__global__ void __launch_bounds__(256) gnn_propagate_kernel(const float* __restrict__ A, int64_t ld, const int32_t* __restrict__ rank,
+                                                             const float* __restrict__ S, int k1, int k2, int64_t N,
+                                                             float* __restrict__ out) {
+  const int64_t i = blockIdx.y;
+  const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (f >= N) return;
+  float sum = 0.f;
+  for (int j = 0; j < k2; ++j) {
+    const int32_t nb = rank[i * k1 + j];
+    if (nb >= 0) sum += A[(int64_t)nb * ld + f] * S[i * k1 + j];
+  }
+  out[i * ld + f] = sum;
+}
+
+__global__ void __launch_bounds__(256) gnn_normalise_kernel(float* __restrict__ A, int64_t ld, int64_t N) {
+  __shared__ float red[8];
+  __shared__ float inv_s;
+  float* row = A + (int64_t)blockIdx.x * ld;
+  float s = 0.f;
+  for (int64_t f = threadIdx.x; f < N; f += 256) s = __fmaf_rn(row[f], row[f], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    inv_s = __fsqrt_rn(t);                               // torch.norm(A, p=2, dim=1): no epsilon (gnn_reranking.py:52-53)
+  }
+  __syncthreads();
+  const float nrm = inv_s;
+  for (int64_t f = threadIdx.x; f < N; f += 256) row[f] = __fdiv_rn(row[f], nrm);
+}
+
+size_t gnn_rerank_workspace_bytes(int64_t N, int32_t k1) {
+  if (N <= 0 || k1 <= 0) return 0;
+  const int64_t ld = round_up(N, 32);
+  return 3 * align256(size_t(N) * k1 * 4) + align256(size_t(N) * ld * 4) + 256;
+}
+
+int gnn_rerank(const float* neg_score, int64_t lds, int64_t N, int32_t k1, int32_t k2, float* A, int64_t ldA, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream) {
+  IEEE_REQUIRE(neg_score && A && workspace, "gnn_rerank: null pointer");
+  IEEE_REQUIRE(N > 0 && lds >= N && ldA >= N && k1 >= 1 && k1 <= N && k1 <= 1024 && k2 >= 1 && k2 <= k1,
+               "gnn_rerank: bad arguments N=%lld k1=%d k2=%d", (long long)N, k1, k2);
+  IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gnn_rerank: workspace must be 256-byte aligned");
+  if (workspace_bytes < gnn_rerank_workspace_bytes(N, k1)) {
+    set_error("gnn_rerank: workspace too small (%zu < %zu)", workspace_bytes, gnn_rerank_workspace_bytes(N, k1));
+    return IEEE_ERR_WORKSPACE;
+  }
+  const int64_t ld = round_up(N, 32);
+  IEEE_REQUIRE(ldA == ld, "gnn_rerank: the adjacency matrix must have a row pitch of %lld floats", (long long)ld);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  int32_t* rank = reinterpret_cast<int32_t*>(w);
+  w += align256(size_t(N) * k1 * 4);
+  float* val = reinterpret_cast<float*>(w);
+  w += align256(size_t(N) * k1 * 4);
+  float* S = reinterpret_cast<float*>(w);
+  w += align256(size_t(N) * k1 * 4);
+  float* B = reinterpret_cast<float*>(w);
+  int rc = topk(neg_score, lds, N, N, 0, nullptr, nullptr, nullptr, nullptr, k1, rank, val, stream);
+  if (rc) return rc;
+  const int64_t nk = N * k1;
+  gnn_square_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(val, S, nk);
+  IEEE_CUDA_CHECK(cudaMemsetAsync(A, 0, size_t(N) * ld * 4, stream));
+  gnn_adjacency_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(rank, k1, N, A, ld);
+  count_launch(2);
+  if (k2 != 1) {
+    const dim3 tgrid((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32)), pgrid((unsigned)((N + 255) / 256), (unsigned)N);
+    for (int it = 0; it < 2; ++it) {
+      gnn_symmetrise_kernel<<<tgrid, 256, 0, stream>>>(A, B, N, ld);
+      gnn_propagate_kernel<<<pgrid, 256, 0, stream>>>(B, ld, rank, S, k1, k2, N, A);
+      gnn_normalise_kernel<<<(unsigned)N, 256, 0, stream>>>(A, ld, N);
+      count_launch(3);
+    }
+  }
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
 }  // namespace ieee

@@ -827,6 +827,18 @@ def evaluate(qf, gf, q_pids, g_pids, q_camids, g_camids, dist_metric="euclidean"
     elif not rerank:
         ev = RetrievalEvaluator(gf, g_pids, g_camids, dist_metric, normalize_feature, precision, max_rank)
         cmc, mAP, _ = ev.evaluate(qf, q_pids, q_camids)
+    elif rerank == "gnn":
+        # alternative re-ranking mode (torchreid/utils/GPU-Re-Ranking/gnn_reranking.py:27-59; its driver L2-normalises
+        # the features and uses k1 = 26, k2 = 7): the negated re-ranked similarity ranks like a distance matrix
+        from .metrics.rank import evaluate_device
+        from .utils.gnn_reranking import gnn_reranking_distmat
+        if verbose:
+            print("Applying GNN re-ranking ...")
+        norm = torch.nn.functional.normalize
+        distmat = gnn_reranking_distmat(norm(qf.float(), dim=1), norm(gf.float(), dim=1), 26, 7)
+        cmc_t, summary, _ = evaluate_device(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
+        raise_for_status(summary, max_rank)
+        cmc, mAP = cmc_t.cpu().numpy(), float(summary.mAP)
     else:
         from .metrics.distance import _device_distmat
         from .metrics.rank import evaluate_device

@@ -33,7 +33,8 @@ def _device_distmat(a: torch.Tensor, b: torch.Tensor, metric: str, normalize: bo
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
     with torch.cuda.device(a.device):
         _lib.call("ieee_distmat", a.data_ptr(), b.data_ptr(), _lib.DTYPES[a.dtype], a.stride(0), b.stride(0), Q, G, D,
-                  _lib.METRICS[metric], int(normalize), prec, out.data_ptr(), out.stride(0), ws.data_ptr(), ws_bytes,
+                  _lib.METRICS.get(metric, _lib.INTERNAL_METRICS.get(metric)), int(normalize), prec, out.data_ptr(),
+                  out.stride(0), ws.data_ptr(), ws_bytes,
                   _lib.stream())
     return out
 

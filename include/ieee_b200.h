@@ -49,7 +49,8 @@ typedef enum {
   IEEE_ERR_CAPACITY = 6        /* a per-query list exceeded the capacity given by the caller   */
 } ieee_status;
 
-typedef enum { IEEE_METRIC_EUCLIDEAN = 0, IEEE_METRIC_COSINE = 1 } ieee_metric;      /* distance.py:36-44 */
+/* distance.py:36-44; NEG_DOT = -(a . b), the similarity GNN re-ranking starts from (gnn_reranking.py:31) as a distance */
+typedef enum { IEEE_METRIC_EUCLIDEAN = 0, IEEE_METRIC_COSINE = 1, IEEE_METRIC_NEG_DOT = 2 } ieee_metric;
 typedef enum { IEEE_DTYPE_F32 = 0, IEEE_DTYPE_BF16 = 1 } ieee_dtype;
 
 /* Arithmetic of the distance contraction (always fp32 accumulation in TMEM / registers):
@@ -327,6 +328,18 @@ size_t ieee_rerank_workspace_bytes(int64_t Q, int64_t G, int32_t k1, int32_t k2)
 int ieee_rerank(const float* q_g, int64_t ld_qg, const float* q_q, int64_t ld_qq, const float* g_g, int64_t ld_gg,
                 int64_t Q, int64_t G, int32_t k1, int32_t k2, double lambda_value, float* out, int64_t ldo,
                 void* workspace, size_t workspace_bytes, ieee_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GNN re-ranking (alternative `rerank` mode).   Replaces torchreid/utils/GPU-Re-Ranking/gnn_reranking.py:27-59 with its
+ * extensions build_adjacency_matrix_kernel.cu:10-17 and gnn_propagate_kernel.cu:8-22.
+ * neg_score: float32 [N, lds] = -(X_u X_u^T) over queries followed by gallery (ieee_distmat with IEEE_METRIC_NEG_DOT),
+ * N = Q + G.  A: float32 [N, ldA] with ldA = N rounded up to 32, receives the propagated, row-normalised adjacency
+ * features; the re-ranked similarity is A[:Q] A[Q:]^T (gnn_reranking.py:55) -- one more contraction by the caller.
+ * k1 <= 1024 neighbours, k2 <= k1 of them propagate (k2 == 1: no propagation, as in the reference).
+ * ---------------------------------------------------------------------------------------------- */
+size_t ieee_gnn_rerank_workspace_bytes(int64_t N, int32_t k1);
+int ieee_gnn_rerank(const float* neg_score, int64_t lds, int64_t N, int32_t k1, int32_t k2, float* A, int64_t ldA,
+                    void* workspace, size_t workspace_bytes, ieee_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Peer exchange: the two exchange steps of a gallery sharded over the GPUs of one box (relevant lists to every rank,

@@ -317,3 +317,33 @@ def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3, stab
     if return_parts:
         return out, {"orig": orig, "rank": rank, "V": V, "jaccard": jaccard}
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# GNN re-ranking  (torchreid/utils/GPU-Re-Ranking/gnn_reranking.py + its two CUDA extensions)
+# PARITY UNPINNED: the reference needs its extensions compiled and a CUDA device, neither of which the build container
+# has, and it ships no vectors; this restatement follows the source line by line and is what the GPU tests check.
+# ----------------------------------------------------------------------------------------------
+def gnn_reranking(X_q, X_g, k1, k2, return_similarity: bool = False):
+    """gnn_reranking.py:27-59.  Neighbour ties go to the lower index (torch.topk leaves them undefined)."""
+    X_q, X_g = np.asarray(X_q, dtype=np.float32), np.asarray(X_g, dtype=np.float32)
+    Q = X_q.shape[0]
+    X_u = np.concatenate((X_q, X_g), 0)
+    score = X_u @ X_u.T                                            # :31
+    rank = np.argsort(-score, axis=1, kind="stable")[:, :k1]       # :36-38 (largest first, sorted)
+    S = np.take_along_axis(score, rank, 1)
+    N = score.shape[0]
+    A = np.zeros((N, N), dtype=np.float32)                          # build_adjacency_matrix_kernel.cu:10-17
+    A[np.arange(N)[:, None], rank] = 1.0
+    S = S * S                                                       # :42
+    if k2 != 1:
+        for _ in range(2):                                          # :45-53
+            A = A + A.T
+            out = np.zeros_like(A)
+            for j in range(k2):                                     # gnn_propagate_kernel.cu:13-20, summed in j order
+                out += A[rank[:, j]] * S[:, j:j + 1]
+            A = out / np.sqrt((out.astype(np.float64) ** 2).sum(1, keepdims=True)).astype(np.float32)
+    cos = A[:Q] @ A[Q:].T                                           # :55
+    if return_similarity:
+        return cos
+    return np.argsort(-cos, axis=1, kind="stable")                  # :58-59

@@ -90,3 +90,29 @@ def test_engine_evaluate_with_rerank(capsys):
     gg = R.compute_distance_matrix(s.gf, s.gf).numpy()
     cmc_o, map_o = R.evaluate_rank(R.re_ranking(qg, qq, gg), s.q_pids, s.g_pids, s.q_camids, s.g_camids)
     assert abs(mAP - map_o) < 5e-3
+
+
+@pytest.mark.parametrize("k1,k2", [(26, 7), (10, 1), (20, 6)])
+def test_gnn_reranking_matches_restatement(k1, k2):
+    """GNN re-ranking (gnn_reranking.py:27-59) against the oracle restatement on L2-normalised features, as the
+    reference's own driver feeds it: re-ranked similarity within 1e-5, ranked lists equal except where the
+    restatement's similarities of the swapped candidates are within 1e-4 of each other."""
+    from ieee_b200.utils.gnn_reranking import gnn_reranking, gnn_reranking_distmat
+    s = make_retrieval_set(60, 300, 12, 3, dim=256, sigma=1.5, seed=k1)
+    xq = torch.nn.functional.normalize(s.qf, dim=1)
+    xg = torch.nn.functional.normalize(s.gf, dim=1)
+    cos_o = R.gnn_reranking(xq.numpy(), xg.numpy(), k1, k2, return_similarity=True)
+    d = gnn_reranking_distmat(xq.cuda(), xg.cuda(), k1, k2).cpu().numpy()
+    assert d.shape == (60, 300) and np.abs(-d - cos_o).max() < 1e-5
+    L = gnn_reranking(xq, xg, k1, k2)
+    L_o = R.gnn_reranking(xq.numpy(), xg.numpy(), k1, k2)
+    assert L.shape == L_o.shape == (60, 300) and L.dtype == np.int64
+    differ = L != L_o                                     # exact ties (the many zeros) go by index on both sides
+    a, b = np.take_along_axis(cos_o, L, 1), np.take_along_axis(cos_o, L_o, 1)
+    assert differ.mean() < 0.05 and np.abs(a - b)[differ].max(initial=0.0) < 1e-4   # only near-ties may swap
+    # as a rerank mode: the negated similarity ranks like a distance matrix
+    cmc, mAP = evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    cmc_o, map_o = R.evaluate_rank(d, s.q_pids, s.g_pids, s.q_camids, s.g_camids)
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - map_o) < 1e-9
+    with pytest.raises(ValueError):
+        gnn_reranking_distmat(xq.cuda(), xg.cuda(), 5, 6)
