@@ -160,64 +160,60 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
   }
 }
 
-// Same arithmetic, one pass over HBM: the whole row lives in registers (NV float4 per lane, rows of up to NV * 128
-// floats), so the normalisation sums, the row maximum and the split all work on the loaded copy, and every lane has
-// NV independent 16-byte loads in flight.  fp32 rows with D % 4 == 0 and 16-byte alignment; identical results to
-// pack_rows_kernel (same per-lane element order in every reduction).
-template <int NV>
-__global__ void __launch_bounds__(256) pack_rows_reg_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
-                                                             int n_norm, int mode, const float* __restrict__ center,
-                                                             uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                                             float* __restrict__ f32, float* __restrict__ norms,
-                                                             float* __restrict__ row_scale) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Same arithmetic, one pass over HBM: the (normalised, centred) row is parked in shared memory between the reduction
+// passes and the split, so global memory is read once per row; loops stay rolled (a fully unrolled register-resident
+// variant stalled on instruction fetch: ncu, stall no_instruction 5.1 per issue).  fp32 rows with D % 4 == 0 and
+// 16-byte alignment; identical results to pack_rows_kernel (same per-lane element order in every reduction).
+__global__ void __launch_bounds__(256) pack_rows_smem_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int D, int Dp,
+                                                              int n_norm, int mode, const float* __restrict__ center,
+                                                              uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                              float* __restrict__ f32, float* __restrict__ norms,
+                                                              float* __restrict__ row_scale) {
+  extern __shared__ __align__(16) float rowbuf_all[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
   if (row >= rows) return;
+  float* buf = rowbuf_all + (size_t)w * Dp;
   const float* xr = x + row * ld;
-  const int nv = Dp / 128 + ((Dp % 128) ? 1 : 0);       // float4 slots per lane that touch the padded row
-  float4 v[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < nv && col < D) v[i] = __ldg(reinterpret_cast<const float4*>(xr + col));
+  // pass 1 (the only read of x): copy the row into shared memory; sum of squares for the first normalisation
+  float s = 0.f;
+#pragma unroll 6
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+    *reinterpret_cast<float4*>(buf + i) = t;
+    s = __fmaf_rn(t.x, t.x, s); s = __fmaf_rn(t.y, t.y, s); s = __fmaf_rn(t.z, t.z, s); s = __fmaf_rn(t.w, t.w, s);
   }
   float den[2] = {1.0f, 1.0f};
-  for (int pass = 0; pass < n_norm; ++pass) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < nv) {
-        float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float u = t[j];
-          if (pass == 1) u = __fdiv_rn(u, den[0]);
-          s = __fmaf_rn(u, u, s);
-        }
-      }
+  if (n_norm >= 1) den[0] = fmaxf(__fsqrt_rn(warp_sum(s)), 1e-12f);
+  if (n_norm >= 2) {
+    s = 0.f;
+#pragma unroll 6
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 t = *reinterpret_cast<const float4*>(buf + i);
+      float u = __fdiv_rn(t.x, den[0]); s = __fmaf_rn(u, u, s);
+      u = __fdiv_rn(t.y, den[0]); s = __fmaf_rn(u, u, s);
+      u = __fdiv_rn(t.z, den[0]); s = __fmaf_rn(u, u, s);
+      u = __fdiv_rn(t.w, den[0]); s = __fmaf_rn(u, u, s);
     }
-    s = warp_sum(s);
-    den[pass] = fmaxf(__fsqrt_rn(s), 1e-12f);
+    den[1] = fmaxf(__fsqrt_rn(warp_sum(s)), 1e-12f);
   }
+  // pass 2: the value the contraction multiplies (normalised, centred), back into the buffer; its largest magnitude
   float amax = 0.f;
+#pragma unroll 4
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 t4 = *reinterpret_cast<const float4*>(buf + i);
+    float t[4] = {t4.x, t4.y, t4.z, t4.w};
+    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (center != nullptr) c4 = __ldg(reinterpret_cast<const float4*>(center + i));
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i < nv) {
-      float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const int col = (i * 32 + lane) * 4;
-      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);      // (the centre is 9 KB: these loads hit L1)
-      if (center != nullptr && col < D) c4 = __ldg(reinterpret_cast<const float4*>(center + col));
-      const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (n_norm >= 1) t[j] = __fdiv_rn(t[j], den[0]);
-        if (n_norm >= 2) t[j] = __fdiv_rn(t[j], den[1]);
-        t[j] = __fsub_rn(t[j], cc[j]);
-        amax = fmaxf(amax, fabsf(t[j]));
-      }
-      v[i] = make_float4(t[0], t[1], t[2], t[3]);       // the value the contraction multiplies (before scaling)
+    for (int j = 0; j < 4; ++j) {
+      if (n_norm >= 1) t[j] = __fdiv_rn(t[j], den[0]);
+      if (n_norm >= 2) t[j] = __fdiv_rn(t[j], den[1]);
+      t[j] = __fsub_rn(t[j], cc[j]);
+      amax = fmaxf(amax, fabsf(t[j]));
     }
+    *reinterpret_cast<float4*>(buf + i) = make_float4(t[0], t[1], t[2], t[3]);
   }
   int e = 0;
   if (mode == PACK_F16_HILO) {
@@ -228,36 +224,36 @@ __global__ void __launch_bounds__(256) pack_rows_reg_kernel(const float* __restr
     }
   }
   const float down = ldexpf(1.0f, -e);
+  // pass 3: split and store (zero padding beyond D)
   float sq = 0.f;
+#pragma unroll 4
+  for (int i = lane * 4; i < Dp; i += 128) {
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < D) t4 = *reinterpret_cast<const float4*>(buf + i);
+    const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+    uint16_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    if (i < nv && col < Dp) {
-      const float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint16_t h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float u = t[j];
-        if (mode == PACK_BF16) {
-          const __nv_bfloat16 b = __float2bfloat16_rn(t[j]);
-          h[j] = __bfloat16_as_ushort(b);
-          l[j] = 0;
-          u = __bfloat162float(b);
-        } else if (mode == PACK_F16_HILO) {
-          const float y = t[j] * down;
-          const __half hh = __float2half_rn(y);
-          h[j] = __half_as_ushort(hh);
-          l[j] = __half_as_ushort(__float2half_rn(y - __half2float(hh)));
-        }
-        sq = __fmaf_rn(u, u, sq);
+    for (int j = 0; j < 4; ++j) {
+      float u = t[j];
+      if (mode == PACK_BF16) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(t[j]);
+        h[j] = __bfloat16_as_ushort(b);
+        l[j] = 0;
+        u = __bfloat162float(b);
+      } else if (mode == PACK_F16_HILO) {
+        const float y = t[j] * down;
+        const __half hh = __float2half_rn(y);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn(y - __half2float(hh)));
       }
-      const int64_t o = row * (int64_t)Dp + col;
-      if (mode == PACK_F32) {
-        *reinterpret_cast<float4*>(f32 + o) = v[i];
-      } else {
-        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
-        if (mode == PACK_F16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
-      }
+      sq = __fmaf_rn(u, u, sq);
+    }
+    const int64_t o = row * (int64_t)Dp + i;
+    if (mode == PACK_F32) {
+      *reinterpret_cast<float4*>(f32 + o) = t4;
+    } else {
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
+      if (mode == PACK_F16_HILO) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
     }
   }
   sq = warp_sum(sq);
@@ -295,9 +291,11 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
   if (dtype == IEEE_DTYPE_F32) {
     const float* xf = static_cast<const float*>(x);
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xf) & 15) == 0);
-    if (vec && L.Dp <= 24 * 128 && !(g_debug_flags & 64))
-      pack_rows_reg_kernel<24><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
-    else if (vec)
+    const size_t row_smem = size_t(warps) * L.Dp * 4;       // one fp32 row per warp
+    if (vec && row_smem <= 96 * 1024 && !(g_debug_flags & 64)) {
+      IEEE_ENSURE_DYN_SMEM(pack_rows_smem_kernel, row_smem);
+      pack_rows_smem_kernel<<<grid, block, row_smem, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+    } else if (vec)
       pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
     else
       pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
