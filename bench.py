@@ -65,13 +65,20 @@ def bench_config(n_gpus: int) -> dict:
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region, read through NVML by the timing loop itself at a few
-    points between steps (rank 0 only; ~0.1 ms per reading, inside the timed region).  Neither a sampling thread (it
-    competes for the GIL with the loop being timed, and with several ranks everybody waits for the slowest host) nor an
-    `nvidia-smi -lms` child process (its polling slowed a 2-GPU step from 0.9 to 3.4 ms) leaves the step alone."""
+    """SM clock / throttle reasons DURING the timed region, read through NVML (rank 0 only).
 
-    def __init__(self, index: int, enabled: bool = True):
+    mode "thread" (default): a sampling thread reads every few milliseconds while the timing loop runs.  The NVML calls
+    are C calls made through ctypes, so the thread holds the GIL only for the few microseconds between them -- the
+    loop being timed never waits for a reading.  (Readings made BY the loop cost ~40 us each on one GPU but 2 - 40 ms
+    each once several ranks share the node, and rank 0 being late stalls every rank at the next hand-over: N = 4
+    measured 6.6 ms per step that way; an `nvidia-smi -lms` child process slowed a 2-GPU step from 0.9 to 3.4 ms.)
+    mode "loop": readings by the timing loop at steps K/4, K/2, 3K/4.  mode "after": no reading inside the timed
+    region; K more steps of the same load follow it at once and are sampled by the loop (their time is not used)."""
+
+    def __init__(self, index: int, enabled: bool = True, mode: str | None = None):
         self.samples, self.reasons, self.max_mhz, self.nv = [], set(), None, None
+        self.mode = mode or os.environ.get("IEEE_BENCH_CLOCKS", "thread")
+        self._thread, self._stop = None, None
         if not enabled:
             return
         try:
@@ -102,10 +109,35 @@ class ClockSampler:
         except Exception:
             pass
 
+    def start(self):
+        """Called right after the start event is recorded."""
+        if self.nv is None or self.mode != "thread":
+            return
+        import threading
+        self._stop = threading.Event()
+
+        def run():
+            while not self._stop.is_set():
+                self.sample()
+                self._stop.wait(0.003)
+
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        """Called right after the stop event is recorded (the GPU is still working through the queue)."""
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
     def result(self):
+        how = {"thread": "NVML readings by a sampling thread (every ~3 ms) while the timed region runs",
+               "loop": "NVML readings taken by the timing loop between steps of the timed region",
+               "after": "NVML readings between steps of a second pass of the same K steps that follows the timed region at once "
+                        "(no reading inside the timed region itself)"}[self.mode]
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "how": "NVML readings taken by the timing loop between steps of the timed region"}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": how}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -444,23 +476,33 @@ def run_ours(args):
         return ev.evaluate(qf_host, lab_host[0], lab_host[1])
 
     def timed(fn, steps, warmup):
+        # NVML is opened BEFORE the barrier: its first queries take 8 - 100 ms, and with that between the barrier and
+        # rank 0's start event the other ranks' clocks were already running while they waited for rank 0's lists
+        # (N = 2 read 1.29 ms per step instead of 0.88; N = 4 once 6.6 ms)
+        sampler = ClockSampler(local_rank, enabled=rank == 0)      # rank 0 samples; the others stay quiet
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank, enabled=rank == 0)      # rank 0 samples; the others stay quiet
-        at = {steps // 4, steps // 2, (3 * steps) // 4}
+        at = {steps // 4, steps // 2, (3 * steps) // 4} if sampler.mode == "loop" else set()
         l0 = lib.ieee_launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
+        sampler.start()
         for i in range(steps):
             out = fn()
             if i in at:
                 sampler.sample()
         stop.record()
+        sampler.stop()
+        launches = lib.ieee_launch_count() - l0
+        if sampler.mode == "after":
+            for i in range(steps):
+                fn()
+                if i in {steps // 4, steps // 2, (3 * steps) // 4}:
+                    sampler.sample()
         barrier()
         clocks = sampler.result()
         ms = start.elapsed_time(stop)
-        launches = lib.ieee_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)

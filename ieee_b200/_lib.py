@@ -31,6 +31,9 @@ SIGNATURES = {
     "ieee_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ieee_set_cta_group": (C.c_int, [C.c_int]),
     "ieee_launch_count": (i64, []),
+    "ieee_note_launches": (i64, [i64]),
+    "ieee_debug_timeline_reset": (None, []),
+    "ieee_debug_timeline": (C.c_int, [C.c_char_p, sz]),
     "ieee_set_debug_flags": (C.c_int, [C.c_int]),
     "ieee_set_raster_panel": (C.c_int, [C.c_int]),
     "ieee_set_centering": (C.c_int, [C.c_int]),

@@ -22,7 +22,33 @@ int g_accum_chunk_kb = 6;
 int g_raster_panel = 0;
 int g_fused_chunk_kb = 0;
 static int g_centering = 1;
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Step timeline (debug flag 128): every named launch on the traced stream is followed by an event record, so the gaps
+// between consecutive marks are kernel time + launch gap as they occur INSIDE a step (ncu serialises and cools the
+// caches; this does not).  ieee_debug_timeline() formats the marks.
+struct TlMark { cudaEvent_t ev; const char* name; };
+static thread_local TlMark tl_marks[96];
+static thread_local int tl_n = 0;
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local bool tl_on = false;
+static void tl_mark(const char* name) {
+  if (!tl_on || tl_n >= 96) return;
+  TlMark& m = tl_marks[tl_n];
+  if (m.ev == nullptr && cudaEventCreate(&m.ev) != cudaSuccess) return;
+  if (cudaEventRecord(m.ev, tl_stream) != cudaSuccess) return;
+  m.name = name;
+  ++tl_n;
+}
+static void tl_enter(cudaStream_t stream, const char* what) {
+  tl_on = (g_debug_flags & 128) != 0;
+  if (!tl_on) return;
+  tl_stream = stream;
+  tl_mark(what);
+}
+void count_launch(int n, const char* name) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  if (name != nullptr && tl_on) tl_mark(name);
+}
 
 int sm_count() {
   static int cached[64] = {0};
@@ -176,6 +202,25 @@ int ieee_set_debug_flags(int flags) {
   const int prev = g_debug_flags;
   g_debug_flags = flags;
   return prev;
+}
+
+int64_t ieee_note_launches(int64_t n) { return g_launches.fetch_add(n) + n; }
+
+void ieee_debug_timeline_reset(void) { tl_n = 0; }
+
+// "name<TAB>us since the previous mark<TAB>us since the first mark" per line; returns the number of marks
+int ieee_debug_timeline(char* buf, size_t cap) {
+  if (buf && cap) buf[0] = 0;
+  if (tl_n == 0) return 0;
+  if (cudaEventSynchronize(tl_marks[tl_n - 1].ev) != cudaSuccess) return -1;
+  size_t off = 0;
+  for (int i = 0; i < tl_n; ++i) {
+    float d = 0.f, t = 0.f;
+    if (i > 0) cudaEventElapsedTime(&d, tl_marks[i - 1].ev, tl_marks[i].ev);
+    cudaEventElapsedTime(&t, tl_marks[0].ev, tl_marks[i].ev);
+    if (buf && off < cap) off += (size_t)snprintf(buf + off, cap - off, "%s\t%.1f\t%.1f\n", tl_marks[i].name, d * 1e3f, t * 1e3f);
+  }
+  return tl_n;
 }
 
 int ieee_set_raster_panel(int m_tiles) {
@@ -422,6 +467,7 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
   IEEE_REQUIRE(gf && g_packed && G > 0 && D > 0, "gallery_prepare: bad arguments (G=%lld D=%lld)", (long long)G, (long long)D);
   IEEE_REQUIRE(center_src == nullptr || (center != nullptr && workspace != nullptr && rows_src > 0),
                "gallery_prepare: a centre source needs the centre buffer and the workspace");
+  tl_enter(stream, "enter gallery_prepare");
   SideLane* lane = nullptr;
   const bool grouping = g_pids != nullptr && group != nullptr;
   if (grouping) {
@@ -435,7 +481,10 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
       (rc = feature_center(center_src, dtype, ld_src, rows_src, D, normalize, 0, center, workspace, stream)))
     return rc;
   if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, center, g_packed, stream))) return rc;
-  if (grouping) IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
+  if (grouping) {
+    IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
+    count_launch(0, "join grouping (side stream)");
+  }
   return IEEE_OK;
 }
 
@@ -520,6 +569,7 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
   void* fix = a.take(distmat_fixup_bytes(Q));
   if (!q_packed || !scratch || !fix) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
+  tl_enter(stream, "enter retrieve_eval_prepared");
   if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
   if (cap <= 0) {
     int32_t need = 0;
@@ -540,6 +590,7 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   }
   if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
   IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
+  count_launch(0, "memset scratch");
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
@@ -811,9 +862,11 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
               ieee_retrieve_prepared_peer_workspace_bytes(Q, D, precision, cap), cap);
     return IEEE_ERR_WORKSPACE;
   }
+  tl_enter(stream, "enter retrieve_eval_prepared_peer");
   if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
   if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
   IEEE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 256, stream));
+  count_launch(0, "memset stats");
   if ((rc = ieee_rank_gather_peer(distmat, ld, G, q_pids, q_camids, g_camids, group, g_offset, n_rel, junk, n_junk, stats, ex,
                                   stream_)))
     return rc;

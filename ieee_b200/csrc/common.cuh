@@ -53,7 +53,7 @@ const char* get_error();
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
-void count_launch(int n = 1);
+void count_launch(int n = 1, const char* name = nullptr);   // a name puts the launch on the step timeline (debug flag 128)
 extern int g_debug_flags;       // ieee_set_debug_flags()
 extern int g_fused_chunk_kb;    // accumulation chunk of the fused-count contraction (0 = as the store kernel)
 extern int g_raster_panel;      // ieee_set_raster_panel(): m tiles per raster panel of the contraction (0 = sized for L2)

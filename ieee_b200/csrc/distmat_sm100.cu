@@ -877,7 +877,7 @@ static int launch_umma(const void* q_packed, int64_t Q, const void* g_packed, in
   cudaLaunchAttribute attr[1];
   cluster_launch_config(cfg, attr, L.groups * CG, kThreads, Cfg::kSmemBytes, CG, stream);
   IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_kernel<CG>, L.ta_hi, L.ta_lo, L.tb_hi, L.tb_lo, L.t_out, L.p));
-  count_launch();
+  count_launch(1, "distmat_umma_kernel");
   return IEEE_OK;
 }
 
@@ -906,6 +906,7 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
     L.p.fix_cap = (uint32_t)(2 * Q + 4096);
     L.p.fix_tau = kFixTau;
     IEEE_CUDA_CHECK(cudaMemsetAsync(fix_ws, 0, 8, stream));
+    count_launch(0, "memset fix list");
   }
   IEEE_ENSURE_DYN_SMEM((distmat_umma_chunked_kernel<CG, FUSED>), Cfg::kSmemBytes);
   cudaLaunchConfig_t cfg;
@@ -913,7 +914,7 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
   cluster_launch_config(cfg, attr, L.groups * CG, kThreadsC, Cfg::kSmemBytes, CG, stream);
   IEEE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distmat_umma_chunked_kernel<CG, FUSED>, L.ta_hi, L.ta_lo, L.tb_hi, L.tb_lo, L.t_out, L.p,
                                      chunk_kb));
-  count_launch();
+  count_launch(1, FUSED ? "distmat_umma_chunked_kernel (counting epilogue)" : "distmat_umma_chunked_kernel");
   if (fix) {
     PackedLayout lq = packed_layout(Q, D, precision), lg = packed_layout(G, D, precision);
     const uint8_t* qb = static_cast<const uint8_t*>(q_packed);
@@ -924,7 +925,7 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
         reinterpret_cast<const float*>(qb + lq.scale_off), reinterpret_cast<const float*>(gb + lg.scale_off),
         reinterpret_cast<const float*>(qb + lq.norm_off), reinterpret_cast<const float*>(gb + lg.norm_off), (int)lq.Dp, (int)G,
         kFixTau, L.p.fix_list, L.p.fix_cap, out, ldo);
-    count_launch();
+    count_launch(1, "distmat_fixup_kernel");
     IEEE_CUDA_CHECK(cudaGetLastError());
   }
   return IEEE_OK;

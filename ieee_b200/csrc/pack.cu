@@ -303,7 +303,7 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
     pack_rows_kernel<__nv_bfloat16, 1><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, (int)D,
                                                                    (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
   }
-  count_launch();
+  count_launch(1, "pack_rows kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -375,7 +375,7 @@ int feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D
     center_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, stride, n_s, (int)D, center);
   else
     center_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, stride, n_s, (int)D, center);
-  count_launch();
+  count_launch(1, "center_rows_kernel");
   if (normalize) {
     center_unit_kernel<<<1, 1024, 0, stream>>>((int)D, center);
     count_launch();

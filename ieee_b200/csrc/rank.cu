@@ -915,7 +915,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
     const unsigned grid = team ? (unsigned)Q : (unsigned)((Q + kWarpQ - 1) / kWarpQ);
     kern<<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel,
                                                junk, n_junk, counts, ties, pv);
-    count_launch();
+    count_launch(1, "rank_count_warp_kernel");
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
   }
@@ -925,7 +925,7 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   IEEE_ENSURE_DYN_SMEM(rank_count_kernel, smem);
   rank_count_kernel<<<(unsigned)Q, kCountThreads, smem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, Rp, rel_all,
                                                                   n_rel, junk, n_junk, counts, ties, pv);
-  count_launch();
+  count_launch(1, "rank_count_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -943,7 +943,7 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
   rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.keys, v.cnt,
                                                                   v.off, v.members, v.T, g_offset, cap, rel, n_rel, junk, n_junk,
                                                                   overflow, pv);
-  count_launch();
+  count_launch(1, "rank_gather_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -1020,7 +1020,7 @@ int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank,
   IEEE_REQUIRE(peers && peers->shards >= 1 && local_stats, "rank_owner_metrics: needs a peer exchange");
   if (max_rank > G_total) max_rank = (int32_t)G_total;
   rank_owner_metrics_kernel<<<(unsigned)((peers->Qown + 127) / 128), 128, 0, stream>>>(*peers, G_total, max_rank, local_stats);
-  count_launch();
+  count_launch(1, "rank_owner_metrics_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -1113,7 +1113,7 @@ int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_
   IEEE_REQUIRE(Q > 0 && G_total > 0 && max_rank >= 1 && shards >= 1 && cap >= 1, "rank_query_metrics: bad shape");
   if (max_rank > G_total) max_rank = (int32_t)G_total;   // rank.py:110-115
   rank_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, stream>>>(counts, Q, G_total, shards, cap, max_rank, ap,
-                                                                     first, short_list, inp); count_launch();
+                                                                     first, short_list, inp); count_launch(1, "rank_query_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }
@@ -1127,7 +1127,7 @@ int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_lis
   const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
   IEEE_ENSURE_DYN_SMEM(rank_reduce_kernel, smem);
   rank_reduce_kernel<<<1, 1024, smem, stream>>>(ap, first, short_list, Q, max_rank, ties, cmc, summary, inp, overflow, pv, stats_out);
-  count_launch();
+  count_launch(1, "rank_reduce_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
 }

@@ -85,10 +85,20 @@ int ieee_set_centering(int on);
 /* Diagnostics for kernel tuning (results are WRONG when non-zero): bit 0 = tensor-core epilogue skips its global
  * stores, bit 1 = epilogue also skips the TMEM reads, bit 2 = no TMA store, bit 3 = chunk BF16 mode too, bit 4 = count
  * stage always uses the CTA-per-query kernel with shared atomics (results stay correct), bit 5 = no near-duplicate
- * fix-up pass (results stay within the accumulator's floor).  Returns the previous value. */
+ * fix-up pass (results stay within the accumulator's floor), bit 7 = step timeline (results stay correct): the
+ * one-call entry points record a CUDA event after every launch they make on the caller's stream.  Returns the
+ * previous value. */
 int ieee_set_debug_flags(int flags);
-/* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
+/* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta).
+ * ieee_note_launches adds n to it -- for a caller that replays a captured CUDA graph of this library's launches,
+ * which the library cannot see -- and returns the new count. */
 int64_t ieee_launch_count(void);
+int64_t ieee_note_launches(int64_t n);
+/* Step timeline (debug bit 7), per calling thread: _reset forgets the marks; ieee_debug_timeline waits for the last
+ * mark and writes one line per mark, "name\tus since the previous mark\tus since the first mark", into buf (NUL
+ * terminated, truncated to cap).  Returns the number of marks, -1 on a CUDA error.  At most 96 marks are kept. */
+void ieee_debug_timeline_reset(void);
+int ieee_debug_timeline(char* buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Distance matrix.   Replaces distance.py:49-64 (euclidean_squared_distance: ||a||^2 + ||b||^2 - 2ab^T,
