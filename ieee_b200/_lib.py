@@ -98,8 +98,7 @@ SIGNATURES.update({
     "ieee_peer_free": (C.c_int, [vp]),
     "ieee_rank_gather_peer": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, _PEER, vp]),
     "ieee_rank_count_peer": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, _PEER, vp]),
-    "ieee_rank_owner_metrics_peer": (C.c_int, [i64, i32, vp, _PEER, vp]),
-    "ieee_rank_reduce_peer": (C.c_int, [i32, vp, vp, vp, _PEER, vp]),
+    "ieee_rank_metrics_peer": (C.c_int, [i64, i32, vp, vp, vp, vp, _PEER, vp]),
     "ieee_peer_result_offset": (sz, [C.c_int, i64, i64, i32, i32, i32]),
     "ieee_retrieve_prepared_peer_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval_prepared_peer": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, i64, i64,

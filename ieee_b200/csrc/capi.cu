@@ -64,12 +64,12 @@ int sm_count() {
 
 // implemented in the other translation units
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
-                  const float* center, void* packed, cudaStream_t stream);
+                  const float* center, void* packed, cudaStream_t stream, const ZeroJob* zero = nullptr);
 size_t feature_center_workspace_bytes(int64_t D);
 int feature_center(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int normalize, int64_t max_rows,
                    float* center, void* workspace, cudaStream_t stream);
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
-                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws);
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws, bool fix_zeroed = false);
 size_t distmat_fixup_bytes(int64_t Q);
 int distmat_simt(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, float* out,
                  int64_t ldo, cudaStream_t stream);
@@ -83,8 +83,8 @@ size_t rank_count_smem(int shards, int cap);
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream, const PeerView* peers = nullptr);
-int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
-                       cudaStream_t stream);
+int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
+                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream);
 int rank_count_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
                    const int64_t* g_camids, const void* group, int32_t cap, int32_t* counts, unsigned long long* ties,
                    int32_t* overflow, cudaStream_t stream);
@@ -98,7 +98,7 @@ int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_lis
 int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                   double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream,
-                  const int32_t* overflow = nullptr);
+                  const int32_t* overflow = nullptr, uint32_t* ticket = nullptr);
 int topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
          const int64_t* q_camids, const int64_t* g_pids, const int64_t* g_camids, int32_t k, int32_t* idx, float* val,
          cudaStream_t stream);
@@ -272,8 +272,8 @@ static size_t center_bytes(int64_t D) { return align256(size_t(D) * 4) + feature
 
 size_t ieee_distmat_fixup_bytes(int64_t Q) { return Q > 0 ? distmat_fixup_bytes(Q) : 0; }
 
-int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
-                        int precision, float* out, int64_t ldo, void* fixup_workspace, ieee_stream_t stream) {
+static int distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                          int precision, float* out, int64_t ldo, void* fixup_workspace, ieee_stream_t stream, bool fix_zeroed) {
   int rc = check_device();
   if (rc) return rc;
   IEEE_REQUIRE(q_packed && g_packed && out, "distmat: null pointer");
@@ -286,7 +286,12 @@ int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, i
   IEEE_REQUIRE(precision == IEEE_PREC_F16X3 || precision == IEEE_PREC_BF16, "unknown precision %d", precision);
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(fixup_workspace) & 7) == 0, "distmat: fix-up workspace must be 8-byte aligned");
   return distmat_umma(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, (cudaStream_t)stream, cta_group_default(),
-                      fixup_workspace);
+                      fixup_workspace, fix_zeroed);
+}
+
+int ieee_distmat_packed(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
+                        int precision, float* out, int64_t ldo, void* fixup_workspace, ieee_stream_t stream) {
+  return distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, fixup_workspace, stream, false);
 }
 
 size_t ieee_distmat_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision) {
@@ -449,7 +454,8 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
-  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
+  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream, nullptr,
+                       reinterpret_cast<uint32_t*>(scratch + 8));
 }
 
 // ---- gallery preparation in one call ----------------------------------------------------------------------
@@ -473,15 +479,17 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
   if (grouping) {
     if ((rc = side_lane(&lane))) return rc;
     IEEE_CUDA_CHECK(cudaEventRecord(lane->fork, stream));
-    IEEE_CUDA_CHECK(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
-    if ((rc = gallery_group(g_pids, G, group, lane->stream))) return rc;
-    IEEE_CUDA_CHECK(cudaEventRecord(lane->join, lane->stream));
   }
+  // the bandwidth-bound kernels are issued FIRST: the six API calls of the side lane took ~25 us of host time during
+  // which the GPU had nothing to do (profiles/r2_step_marks.txt)
   if (center_src != nullptr &&
       (rc = feature_center(center_src, dtype, ld_src, rows_src, D, normalize, 0, center, workspace, stream)))
     return rc;
   if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, center, g_packed, stream))) return rc;
   if (grouping) {
+    IEEE_CUDA_CHECK(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+    if ((rc = gallery_group(g_pids, G, group, lane->stream))) return rc;
+    IEEE_CUDA_CHECK(cudaEventRecord(lane->join, lane->stream));
     IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
     count_launch(0, "join grouping (side stream)");
   }
@@ -523,7 +531,8 @@ int ieee_eval_market1501_f64(const double* distmat, int64_t ld, int64_t Q, int64
   IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_count_f64(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, cap, counts, ties, scratch + 1, stream))) return rc;
-  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream);
+  return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, nullptr, nullptr, fws, stream, nullptr,
+                       reinterpret_cast<uint32_t*>(scratch + 8));
 }
 
 // ---- retrieval + evaluation in one call ----------------------------------------------------------------
@@ -570,7 +579,9 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   void* fix = a.take(distmat_fixup_bytes(Q));
   if (!q_packed || !scratch || !fix) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
   tl_enter(stream, "enter retrieve_eval_prepared");
-  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
+  // the query pack's first CTA clears the scratch words and the fix-up list header for the kernels behind it
+  const ZeroJob zero{{reinterpret_cast<uint32_t*>(scratch), static_cast<uint32_t*>(fix)}, {64, 2}};
+  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream, &zero))) return rc;
   if (cap <= 0) {
     int32_t need = 0;
     if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
@@ -588,14 +599,13 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
               ieee_retrieve_prepared_workspace_bytes(Q, D, precision, cap), cap);
     return IEEE_ERR_WORKSPACE;
   }
-  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
-  IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256, stream));
-  count_launch(0, "memset scratch");
+  if ((rc = distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_, true))) return rc;
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
+  // scratch: [0] cap, [1] overflow, [2..3] ties, [8] ticket of the metrics kernel (all cleared by the query pack)
   return rank_finalize(counts, Q, G, 1, cap, max_rank, ties, cmc, summary, per_query_ap, per_query_first, fws, stream,
-                       scratch + 1);
+                       scratch + 1, reinterpret_cast<uint32_t*>(scratch + 8));
 }
 
 int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg, int dtype, int64_t Q, int64_t G, int64_t D,
@@ -709,16 +719,15 @@ uint32_t ieee_retrieve_fused_spill_capacity(int64_t Q, int64_t G) { return (Q > 
 // regions are sized for the largest query block (Qb_max); a block of Qb <= Qb_max rows uses a dense prefix of each
 static size_t peer_layout(int64_t Qb_max, int64_t Qb, int64_t Qtot, int32_t cap, int32_t W, int32_t shards, PeerView* v) {
   size_t o = kPeerHeaderBytes;
-  const int64_t Qown_max = (Qb_max + shards - 1) / shards, Qown = (Qb + shards - 1) / shards;
   auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
   const size_t off_rel = take(size_t(shards) * Qb_max * (cap + 1) * 8);
-  const size_t off_cnt = take(size_t(shards) * Qown_max * (W + 2) * 4);
+  const size_t off_cnt = take(size_t(shards) * Qb_max * (W + 2) * 4);
   const size_t off_ap = take(size_t(Qtot) * 8), off_inp = take(size_t(Qtot) * 8);
   const size_t off_first = take(size_t(Qtot) * 4), off_short = take(size_t(Qtot) * 4);
   if (v) {
     v->off_rel = off_rel; v->off_cnt = off_cnt; v->off_ap = off_ap; v->off_inp = off_inp;
     v->off_first = off_first; v->off_short = off_short;
-    v->Qb = Qb; v->Qown = (int)Qown; v->cap = cap; v->W = W;
+    v->Qb = Qb; v->cap = cap; v->W = W;
   }
   return o;
 }
@@ -806,26 +815,14 @@ int ieee_rank_count_peer(const float* distmat, int64_t ld, int64_t G, int64_t g_
                     (cudaStream_t)stream, &v);
 }
 
-int ieee_rank_owner_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats,
-                                 const ieee_peer_exchange* ex, ieee_stream_t stream) {
+int ieee_rank_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats, float* cmc,
+                           ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex, ieee_stream_t stream) {
   int rc = check_device();
   if (rc) return rc;
   PeerView v;
   if ((rc = peer_view(ex, &v))) return rc;
-  return rank_owner_metrics(&v, G_total, max_rank, stats, (cudaStream_t)stream);
-}
-
-int ieee_rank_reduce_peer(int32_t max_rank, float* cmc, ieee_eval_summary* summary, int64_t* stats_out,
-                          const ieee_peer_exchange* ex, ieee_stream_t stream) {
-  int rc = check_device();
-  if (rc) return rc;
-  PeerView v;
-  if ((rc = peer_view(ex, &v))) return rc;
-  uint8_t* mine = v.base[v.my];
-  return rank_reduce(reinterpret_cast<const double*>(mine + v.off_ap), reinterpret_cast<const int32_t*>(mine + v.off_first),
-                     reinterpret_cast<const int32_t*>(mine + v.off_short), ex->Qtot, max_rank, nullptr, cmc, summary,
-                     reinterpret_cast<const double*>(mine + v.off_inp), nullptr, (cudaStream_t)stream, &v,
-                     reinterpret_cast<long long*>(stats_out));
+  return rank_metrics_peer(&v, G_total, max_rank, stats, cmc, summary, reinterpret_cast<long long*>(stats_out), ex->Qtot,
+                           (cudaStream_t)stream);
 }
 
 size_t ieee_retrieve_prepared_peer_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap) {
@@ -863,16 +860,14 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
     return IEEE_ERR_WORKSPACE;
   }
   tl_enter(stream, "enter retrieve_eval_prepared_peer");
-  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream))) return rc;
-  if ((rc = ieee_distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_))) return rc;
-  IEEE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 256, stream));
-  count_launch(0, "memset stats");
+  const ZeroJob zero{{reinterpret_cast<uint32_t*>(stats), static_cast<uint32_t*>(fix)}, {64, 2}};
+  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream, &zero))) return rc;
+  if ((rc = distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_, true))) return rc;
   if ((rc = ieee_rank_gather_peer(distmat, ld, G, q_pids, q_camids, g_camids, group, g_offset, n_rel, junk, n_junk, stats, ex,
                                   stream_)))
     return rc;
   if ((rc = ieee_rank_count_peer(distmat, ld, G, g_offset, n_rel, junk, n_junk, stats, ex, stream_))) return rc;
-  if ((rc = ieee_rank_owner_metrics_peer(G_total, max_rank, stats, ex, stream_))) return rc;
-  return ieee_rank_reduce_peer(max_rank > G_total ? (int32_t)G_total : max_rank, cmc, summary, stats_out, ex, stream_);
+  return ieee_rank_metrics_peer(G_total, max_rank, stats, cmc, summary, stats_out, ex, stream_);
 }
 
 size_t ieee_peer_result_offset(int which, int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards) {

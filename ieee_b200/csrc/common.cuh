@@ -53,6 +53,18 @@ const char* get_error();
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 int sm_count();
+// Small scratch words a kernel's first CTA clears on behalf of the kernels that follow it on the stream (a
+// cudaMemsetAsync node between two kernels costs ~4 us of a step; up to 256 words per region).
+struct ZeroJob {
+  uint32_t* p[2];
+  int n[2];
+  __device__ __forceinline__ void run() const {
+    if (blockIdx.x != 0) return;
+    for (int i = 0; i < 2; ++i)
+      if (p[i] != nullptr && (int)threadIdx.x < n[i]) p[i][threadIdx.x] = 0u;
+  }
+};
+
 void count_launch(int n = 1, const char* name = nullptr);   // a name puts the launch on the step timeline (debug flag 128)
 extern int g_debug_flags;       // ieee_set_debug_flags()
 extern int g_fused_chunk_kb;    // accumulation chunk of the fused-count contraction (0 = as the store kernel)
@@ -131,25 +143,31 @@ struct FusedCount {
 
 // ---- exchange between the ranks of a sharded gallery over NVLink peer memory ----------------------------------
 // Every rank owns one exchange buffer (ieee_peer_alloc) that all ranks of the gallery group map (cudaIpc): the rank
-// kernels STORE their lists / partial counts / per-query results straight into the peers' buffers and hand over with
-// flag words, instead of an all-gather + all-reduce per query block.  Header (first 1 KB of a buffer):
+// kernels STORE their lists and partial counts straight into EVERY peer's buffer and hand over with flag words,
+// instead of an all-gather + all-reduce per query block; each rank then derives all per-query results itself (the
+// same integer sums everywhere, so no result broadcast).  Two hand-overs per block are enough, and they also
+// protect the buffers across blocks: a rank that has seen flag B of block n from peer p knows p's count kernel of
+// block n is over (p is done reading its lists: they may be overwritten), and flag A of block n + 1 from p says p's
+// metrics kernel of block n is over (p's count rows may be overwritten).  Header (first 1 KB of a buffer):
 //   [0, 128)    flag A[s]: epoch of the last block whose relevant lists from shard s have landed here
-//   [128, 256)  flag B[s]: ... whose partial counts from shard s have landed here
-//   [256, 384)  flag C[s]: ... whose per-query results from owner s have landed here
+//   [128, 256)  flag B[s]: ... whose partial counts (and statistics) from shard s have landed here
+//   [256, 384)  unused (flag C of the three-phase protocol this replaced)
 //   [384, 408)  sent[3]:   (local) epoch this rank has already signalled per phase
 //   [416, 440)  seen[3]:   (local) epoch for which this rank has already seen every peer's flag of the phase
+//   [448, 452)  ticket of the metrics kernel's last-CTA reduction (zero between kernels)
 //   [512, ...)  stats[s][4]: shard s' {gather overflow, tie pairs, longest merged list, -}
 constexpr int kMaxPeers = 16;
 constexpr size_t kPeerHeaderBytes = 1024;
+constexpr size_t kPeerTicketOffset = 448;   // a word of the header no flag uses: ticket of the metrics kernel's last-CTA reduction
 struct PeerView {
   int shards, my;                  // shards == 0: no peer exchange (single GPU / NCCL path)
   unsigned long long epoch;        // one per query block, increasing
   uint8_t* base[kMaxPeers];        // every rank's buffer as mapped into this process; base[my] is this rank's own
   unsigned long long off_rel;      // uint64 [shards][Qb][cap + 1]   relevant lists (+ length), slot s written by shard s
-  unsigned long long off_cnt;      // int32  [shards][Qown][W + 2]   partial counts of the queries this rank owns
+  unsigned long long off_cnt;      // int32  [shards][Qb][W + 2]     partial counts, slot s written by shard s
   unsigned long long off_ap, off_inp, off_first, off_short;   // per-query results [Qtot]: f64, f64, i32, i32
   long long Qb, q_base;            // rows of this query block; index of its first query in the result arrays
-  int Qown, cap, W;                // queries per owner = ceil(Qb / shards); list capacity; count row width
+  int cap, W;                      // list capacity; count row width
 };
 inline PeerView no_peers() { PeerView v; memset(&v, 0, sizeof(v)); return v; }
 
@@ -179,8 +197,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// Called by every thread of every CTA at the top of the kernel that CONSUMES phase `phase` (0 lists, 1 partial counts,
-// 2 per-query results).  The producing kernel is the previous one on this stream, so all of this rank's stores --
+// Called by every thread of every CTA at the top of the kernel that CONSUMES phase `phase` (0 lists, 1 partial
+// counts).  The producing kernel is the previous one on this stream, so all of this rank's stores --
 // including the ones into peer buffers -- are complete when any CTA of this kernel runs: the first CTA to get here
 // publishes them (fence, then one flag store per peer), then everybody waits until every peer has done the same.
 // `stats_src` (4 words, may be null) is copied into this rank's stats slot of every peer before the flags.

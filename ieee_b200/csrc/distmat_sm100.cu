@@ -890,7 +890,7 @@ size_t distmat_fixup_bytes(int64_t Q) { return align256((size_t(2 * Q + 4096) + 
 template <int CG, bool FUSED>
 static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric,
                                int precision, float* out, int64_t ldo, cudaStream_t stream, int chunk_kb, void* fix_ws,
-                               const FusedCount* fc = nullptr) {
+                               const FusedCount* fc = nullptr, bool fix_zeroed = false) {
   using Cfg = GemmCfgC<CG, FUSED>;
   GemmLaunch L;
   int rc = gemm_setup<CG>(L, q_packed, Q, g_packed, G, D, metric, precision, out, ldo, 16, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -905,8 +905,10 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
     L.p.fix_list = static_cast<unsigned long long*>(fix_ws);
     L.p.fix_cap = (uint32_t)(2 * Q + 4096);
     L.p.fix_tau = kFixTau;
-    IEEE_CUDA_CHECK(cudaMemsetAsync(fix_ws, 0, 8, stream));
-    count_launch(0, "memset fix list");
+    if (!fix_zeroed) {      // (the one-call entry points have an earlier kernel clear the list header)
+      IEEE_CUDA_CHECK(cudaMemsetAsync(fix_ws, 0, 8, stream));
+      count_launch(0, "memset fix list");
+    }
   }
   IEEE_ENSURE_DYN_SMEM((distmat_umma_chunked_kernel<CG, FUSED>), Cfg::kSmemBytes);
   cudaLaunchConfig_t cfg;
@@ -932,12 +934,14 @@ static int launch_umma_chunked(const void* q_packed, int64_t Q, const void* g_pa
 }
 
 int distmat_umma(const void* q_packed, int64_t Q, const void* g_packed, int64_t G, int64_t D, int metric, int precision,
-                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws) {
+                 float* out, int64_t ldo, cudaStream_t stream, int cta_group, void* fix_ws, bool fix_zeroed) {
   // chunked accumulation serves the fp32-grade mode; the 1-pass BF16 mode keeps the whole K in TMEM (throughput mode)
   if (g_accum_chunk_kb > 0 && (precision == IEEE_PREC_F16X3 || (g_debug_flags & 8))) {
     if (cta_group == 2)
-      return launch_umma_chunked<2, false>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws);
-    return launch_umma_chunked<1, false>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws);
+      return launch_umma_chunked<2, false>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws,
+                                           nullptr, fix_zeroed);
+    return launch_umma_chunked<1, false>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream, g_accum_chunk_kb, fix_ws,
+                                         nullptr, fix_zeroed);
   }
   if (cta_group == 2)
     return launch_umma<2>(q_packed, Q, g_packed, G, D, metric, precision, out, ldo, stream);

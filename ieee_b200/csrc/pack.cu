@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
                                                          int n_norm, int mode, const float* __restrict__ center,
                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                                          float* __restrict__ f32, float* __restrict__ norms,
-                                                         float* __restrict__ row_scale) {
+                                                         float* __restrict__ row_scale, const ZeroJob zero) {
+  zero.run();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256) pack_rows_smem_kernel(const float* __rest
                                                               int n_norm, int mode, const float* __restrict__ center,
                                                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                                               float* __restrict__ f32, float* __restrict__ norms,
-                                                              float* __restrict__ row_scale) {
+                                                              float* __restrict__ row_scale, const ZeroJob zero) {
+  zero.run();
   extern __shared__ __align__(16) float rowbuf_all[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
@@ -264,7 +266,8 @@ __global__ void __launch_bounds__(256) pack_rows_smem_kernel(const float* __rest
 }
 
 int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D, int metric, int normalize, int precision,
-                  const float* center, void* packed, cudaStream_t stream) {
+                  const float* center, void* packed, cudaStream_t stream, const ZeroJob* zero) {
+  const ZeroJob zj = zero ? *zero : ZeroJob{{nullptr, nullptr}, {0, 0}};
   IEEE_REQUIRE(x != nullptr && packed != nullptr, "pack_features: null pointer");
   IEEE_REQUIRE(rows >= 0 && D > 0 && ld >= D, "pack_features: bad shape rows=%lld D=%lld ld=%lld", (long long)rows,
                (long long)D, (long long)ld);
@@ -275,7 +278,11 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
   IEEE_REQUIRE(center == nullptr || metric == IEEE_METRIC_EUCLIDEAN,
                "pack_features: a centre only applies to the euclidean metric (cosine is not translation invariant)");
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(center) & 15) == 0, "pack_features: centre must be 16-byte aligned");
-  if (rows == 0) return IEEE_OK;
+  if (rows == 0) {
+    for (int i = 0; i < 2; ++i)
+      if (zj.p[i] && zj.n[i] > 0) IEEE_CUDA_CHECK(cudaMemsetAsync(zj.p[i], 0, size_t(zj.n[i]) * 4, stream));
+    return IEEE_OK;
+  }
   PackedLayout L = packed_layout(rows, D, precision);
   uint8_t* base = static_cast<uint8_t*>(packed);
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 255) == 0, "pack_features: packed buffer must be 256-byte aligned");
@@ -294,14 +301,14 @@ int pack_features(const void* x, int dtype, int64_t ld, int64_t rows, int64_t D,
     const size_t row_smem = size_t(warps) * L.Dp * 4;       // one fp32 row per warp
     if (vec && row_smem <= 96 * 1024 && !(g_debug_flags & 64)) {
       IEEE_ENSURE_DYN_SMEM(pack_rows_smem_kernel, row_smem);
-      pack_rows_smem_kernel<<<grid, block, row_smem, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+      pack_rows_smem_kernel<<<grid, block, row_smem, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale, zj);
     } else if (vec)
-      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+      pack_rows_kernel<float, 4><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale, zj);
     else
-      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+      pack_rows_kernel<float, 1><<<grid, block, 0, stream>>>(xf, ld, rows, (int)D, (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale, zj);
   } else {
     pack_rows_kernel<__nv_bfloat16, 1><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, (int)D,
-                                                                   (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale);
+                                                                   (int)L.Dp, n_norm, mode, center, hi, lo, f32, norms, rscale, zj);
   }
   count_launch(1, "pack_rows kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());

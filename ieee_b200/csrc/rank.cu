@@ -476,6 +476,26 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane,
   for (int g = head + 4 * nvec + t0; g < G; g += S) one(g);
 }
 
+// Where the count kernels put a query's row.  Alone: the caller's table.  With a peer exchange: slot `my` of EVERY
+// rank's table (posted stores over NVLink), so that each rank can sum the shards' partial counts itself and the
+// evaluation needs no third hand-over (an owner stage + result broadcast was one more flag round trip per step).
+struct CountRow {
+  int32_t* local;
+  const PeerView* pv;
+  int64_t slot_row;      // (my * Qb + q) * stride
+  __device__ __forceinline__ void put(int idx, int32_t v) const {
+    if (pv->shards == 0) { local[idx] = v; return; }
+    for (int p = 0; p < pv->shards; ++p) reinterpret_cast<int32_t*>(pv->base[p] + pv->off_cnt)[slot_row + idx] = v;
+  }
+};
+__device__ __forceinline__ CountRow count_row(int32_t* counts, int64_t q, int stride, const PeerView& pv) {
+  CountRow r;
+  r.local = counts ? counts + q * stride : nullptr;
+  r.pv = &pv;
+  r.slot_row = ((int64_t)pv.my * pv.Qb + q) * stride;
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // count kernel.  WPQ = warps per query:
 //   WPQ = 1  eight queries per CTA, one warp each: short rows (G <= 64K), where a CTA-wide setup would cost more
@@ -516,11 +536,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
   const int64_t q = kTeam ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * kWarpQ + w;
   if (q >= Q) return;
   const int stride = out_cap + 2;
-  int32_t* out = counts + q * stride;
-  if (pv.shards) {   // partial counts go to the rank that owns query q (posted stores into its table, slot `my`)
-    const int owner = (int)(q / pv.Qown);
-    out = reinterpret_cast<int32_t*>(pv.base[owner] + pv.off_cnt) + ((int64_t)pv.my * pv.Qown + (q - (int64_t)owner * pv.Qown)) * stride;
-  }
+  const CountRow out = count_row(counts, q, stride, pv);
   const int nj = n_junk[q];
   // list lengths of all shards in ONE round of loads (lane s reads shard s), then a warp scan: with 8 shards the
   // set-up used to pay 8 dependent trips to L2 per query, and set-up is what a short (sharded) row costs
@@ -537,7 +553,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
   }
   if (lane == 0 && wq == 0) {
-    out[stride - 1] = nj; out[stride - 2] = n_rel[q];
+    out.put(stride - 1, nj); out.put(stride - 2, n_rel[q]);
     // longest merged list seen: sizes the next call's rows (out_cap); a list longer than this call's is flagged by it
     if (ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
   }
@@ -700,7 +716,7 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
     for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
     if (k < R) {
       const int64_t gi = (int64_t)(uint32_t)T[k] - g_offset;
-      out[k] = carry + incl - ((gi >= 0 && gi < G) ? 1 : 0);
+      out.put(k, carry + incl - ((gi >= 0 && gi < G) ? 1 : 0));
     }
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
@@ -723,16 +739,12 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   const int stride = out_cap + 2;
-  int32_t* out = counts + q * stride;
-  if (pv.shards) {
-    const int owner = (int)(q / pv.Qown);
-    out = reinterpret_cast<int32_t*>(pv.base[owner] + pv.off_cnt) + ((int64_t)pv.my * pv.Qown + (q - (int64_t)owner * pv.Qown)) * stride;
-  }
+  const CountRow out = count_row(counts, q, stride, pv);
   int Rtot = 0;
   for (int s = 0; s < shards; ++s) Rtot += (int)rel_all[((int64_t)s * Q + q) * (cap + 1) + cap];
   if (tid == 0 && ties_out != nullptr && (unsigned long long)Rtot > ties_out[1]) atomicMax(ties_out + 1, (unsigned long long)Rtot);
   if (Rtot > out_cap) {                      // row too small for this query's merged list: flagged above, caller re-runs
-    if (tid == 0) { out[stride - 1] = n_junk[q]; out[stride - 2] = n_rel[q]; }
+    if (tid == 0) { out.put(stride - 1, n_junk[q]); out.put(stride - 2, n_rel[q]); }
     return;
   }
 
@@ -754,7 +766,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
   }
   const int R = misc[0];
   const int nj = n_junk[q];
-  if (tid == 0) { out[stride - 1] = nj; out[stride - 2] = n_rel[q]; }
+  if (tid == 0) { out.put(stride - 1, nj); out.put(stride - 2, n_rel[q]); }
   if (R == 0) return;   // invalid query (rank.py:142-144): nothing to rank against
   if (stage_in_priv && R <= 512) {
     // rank sort: keys are distinct (distinct gallery indices), so #smaller is each key's final position
@@ -873,7 +885,7 @@ rank_count_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int 
     for (int i = 0; i < w; ++i) woff += wsum[i];
     if (k < R) {
       const int64_t gi = (int64_t)(uint32_t)T[k] - g_offset;
-      out[k] = woff + incl - ((gi >= 0 && gi < G) ? 1 : 0);
+      out.put(k, woff + incl - ((gi >= 0 && gi < G) ? 1 : 0));
     }
     __syncthreads();
     if (tid == kCountThreads - 1) carry = woff + incl;
@@ -951,13 +963,8 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
 // ---------------------------------------------------------------------------------------------------------
 // finalize: per-query AP / first hit, then one deterministic CTA-wide reduction.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restrict__ counts,
-                                                          int64_t Q, int64_t G_total, int shards, int cap, int max_rank,
-                                                          double* __restrict__ ap, int32_t* __restrict__ first,
-                                                          int32_t* __restrict__ is_short, double* __restrict__ inp) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const int stride = shards * cap + 2;
+__device__ __forceinline__ void query_metrics(const int32_t* __restrict__ counts, int64_t q, int64_t G_total, int stride,
+                                              int max_rank, double* ap, int32_t* first, int32_t* is_short, double* inp) {
   const int32_t* c = counts + q * stride;
   const int R = c[stride - 2];            // relevant items over all shards (summed with the counts)
   if (R == 0) {
@@ -976,64 +983,21 @@ __global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restri
   is_short[q] = kept < max_rank ? 1 : 0;
 }
 
-// Peer exchange, middle stage: this rank OWNS queries [my * Qown, (my + 1) * Qown) of the block.  It sums the partial
-// counts the shards stored into its table (integers: exact in any order), derives AP / first hit / mINP term exactly
-// as rank_query_kernel does, and stores the per-query results into EVERY rank's result arrays, so that each rank can
-// run the same deterministic reduction and end with bit-identical (cmc, mAP).
-__global__ void __launch_bounds__(128) rank_owner_metrics_kernel(const PeerView pv, int64_t G_total, int max_rank,
-                                                                  const unsigned long long* __restrict__ local_stats) {
-  peer_signal_and_wait(pv, 1, local_stats);       // every shard's partial counts (and statistics) have landed here
-  const int64_t ql = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t q = (int64_t)pv.my * pv.Qown + ql;
-  if (ql >= pv.Qown || q >= pv.Qb) return;
-  const int stride = pv.W + 2;
-  const int32_t* part = reinterpret_cast<const int32_t*>(pv.base[pv.my] + pv.off_cnt) + ql * stride;
-  const int64_t shard_stride = (int64_t)pv.Qown * stride;
-  int R = 0, nj = 0;
-  for (int s = 0; s < pv.shards; ++s) { R += part[s * shard_stride + stride - 2]; nj += part[s * shard_stride + stride - 1]; }
-  double ap = 0.0, inp = 0.0;
-  int32_t first = -1, is_short = 0;
-  if (R > 0 && R <= pv.W) {                       // (R > W: rows too narrow, flagged through the statistics; rerun)
-    double acc = 0.0;
-    int pos = 0;
-    for (int k = 0; k < R; ++k) {
-      pos = 0;
-      for (int s = 0; s < pv.shards; ++s) pos += part[s * shard_stride + k];
-      if (k == 0) first = pos;
-      acc += (double)(k + 1) / ((double)pos + 1.0);          // rank.py:155-160
-    }
-    ap = acc / (double)R;
-    inp = (double)R / ((double)pos + 1.0);                   // hardest relevant item: the last (largest) position
-    is_short = (G_total - (int64_t)nj) < max_rank ? 1 : 0;
-  }
-  const int64_t gq = pv.q_base + q;
-  for (int p = 0; p < pv.shards; ++p) {
-    reinterpret_cast<double*>(pv.base[p] + pv.off_ap)[gq] = ap;
-    reinterpret_cast<double*>(pv.base[p] + pv.off_inp)[gq] = inp;
-    reinterpret_cast<int32_t*>(pv.base[p] + pv.off_first)[gq] = first;
-    reinterpret_cast<int32_t*>(pv.base[p] + pv.off_short)[gq] = is_short;
-  }
+__global__ void __launch_bounds__(256) rank_query_kernel(const int32_t* __restrict__ counts,
+                                                          int64_t Q, int64_t G_total, int shards, int cap, int max_rank,
+                                                          double* __restrict__ ap, int32_t* __restrict__ first,
+                                                          int32_t* __restrict__ is_short, double* __restrict__ inp) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  query_metrics(counts, q, G_total, shards * cap + 2, max_rank, ap, first, is_short, inp);
 }
 
-int rank_owner_metrics(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
-                       cudaStream_t stream) {
-  IEEE_REQUIRE(peers && peers->shards >= 1 && local_stats, "rank_owner_metrics: needs a peer exchange");
-  if (max_rank > G_total) max_rank = (int32_t)G_total;
-  rank_owner_metrics_kernel<<<(unsigned)((peers->Qown + 127) / 128), 128, 0, stream>>>(*peers, G_total, max_rank, local_stats);
-  count_launch(1, "rank_owner_metrics_kernel");
-  IEEE_CUDA_CHECK(cudaGetLastError());
-  return IEEE_OK;
-}
-
-__global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restrict__ ap, const int32_t* __restrict__ first,
-                                                            const int32_t* __restrict__ is_short, int64_t Q, int max_rank,
-                                                            const unsigned long long* __restrict__ ties, float* __restrict__ cmc,
-                                                            ieee_eval_summary* __restrict__ summary,
-                                                            const double* __restrict__ inp,
-                                                            const int32_t* __restrict__ overflow, const PeerView pv,
-                                                            long long* __restrict__ stats_out) {
-  extern __shared__ __align__(16) uint8_t rs_raw[];
-  if (pv.shards) peer_signal_and_wait(pv, 2);      // every owner's per-query results have landed in this rank's arrays
+// The reduction proper, run by ONE CTA of 1024 threads (a kernel of its own, or the last CTA of the metrics kernels).
+// No __restrict__ / read-only loads here: the arrays may have been written earlier in the same kernel.
+__device__ __forceinline__ void reduce_body(uint8_t* rs_raw, const double* ap, const int32_t* first, const int32_t* is_short,
+                                            int64_t Q, int max_rank, const unsigned long long* ties, float* cmc,
+                                            ieee_eval_summary* summary, const double* inp, const int32_t* overflow,
+                                            const PeerView& pv, long long* stats_out) {
   double* sd = reinterpret_cast<double*>(rs_raw);                 // [1024] AP partial sums
   double* si = sd + 1024;                                         // [1024] INP partial sums
   int32_t* hfirst = reinterpret_cast<int32_t*>(si + 1024);        // [max_rank + 1]
@@ -1104,6 +1068,106 @@ __global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restr
   }
 }
 
+__global__ void __launch_bounds__(1024) rank_reduce_kernel(const double* __restrict__ ap, const int32_t* __restrict__ first,
+                                                            const int32_t* __restrict__ is_short, int64_t Q, int max_rank,
+                                                            const unsigned long long* __restrict__ ties, float* __restrict__ cmc,
+                                                            ieee_eval_summary* __restrict__ summary,
+                                                            const double* __restrict__ inp,
+                                                            const int32_t* __restrict__ overflow, const PeerView pv,
+                                                            long long* __restrict__ stats_out) {
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  reduce_body(rs_raw, ap, first, is_short, Q, max_rank, ties, cmc, summary, inp, overflow, pv, stats_out);
+}
+
+// True in exactly one CTA of the grid: the one that finishes last.  Its threads then see every other CTA's global
+// writes (fence, ticket, fence).  The ticket word must be zero at launch; the last CTA leaves it zero again.
+__device__ __forceinline__ bool last_cta_done(uint32_t* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  return true;
+}
+
+// rank_query_kernel and rank_reduce_kernel in ONE launch (a launch boundary is 3 - 6 us of a 0.75 ms step): CTAs of
+// 1024 threads derive the per-query results, the CTA that finishes last runs the reduction -- the same fixed
+// assignment and tree as rank_reduce_kernel, so the sums come out bit-identical to the two-kernel form.
+//
+// With a peer exchange (pv.shards > 0) the kernel first hands over / waits for the shards' partial counts (phase B;
+// this rank's statistics travel with the signal), sums them per query (integers: exact in any order) and reduces
+// over all Qtot queries when `reduce_now` says this was the last block.  Every rank does the same arithmetic on the
+// same integers, so (cmc, mAP) come out bit-identical everywhere without a result broadcast.
+__global__ void __launch_bounds__(1024) rank_metrics_kernel(const int32_t* __restrict__ counts, int64_t Q, int64_t G_total, int stride,
+                                                             int max_rank, double* ap, int32_t* first, int32_t* is_short,
+                                                             double* inp, const unsigned long long* ties, float* cmc,
+                                                             ieee_eval_summary* summary, const int32_t* overflow, uint32_t* ticket,
+                                                             const PeerView pv, const unsigned long long* local_stats,
+                                                             long long* stats_out, int reduce_now, int64_t Qred) {
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pv.shards) {
+    peer_signal_and_wait(pv, 1, local_stats);       // every shard's partial counts (and statistics) have landed here
+    if (q < Q) {
+      const int32_t* part = reinterpret_cast<const int32_t*>(pv.base[pv.my] + pv.off_cnt) + q * stride;
+      const int64_t shard_stride = (int64_t)pv.Qb * stride;
+      int R = 0, nj = 0;
+      for (int s = 0; s < pv.shards; ++s) { R += part[s * shard_stride + stride - 2]; nj += part[s * shard_stride + stride - 1]; }
+      double a = 0.0, np = 0.0;
+      int32_t f = -1, sh = 0;
+      if (R > 0 && R <= pv.W) {                       // (R > W: rows too narrow, flagged through the statistics; rerun)
+        double acc = 0.0;
+        int pos = 0;
+        for (int k = 0; k < R; ++k) {
+          pos = 0;
+          for (int s = 0; s < pv.shards; ++s) pos += part[s * shard_stride + k];
+          if (k == 0) f = pos;
+          acc += (double)(k + 1) / ((double)pos + 1.0);          // rank.py:155-160
+        }
+        a = acc / (double)R;
+        np = (double)R / ((double)pos + 1.0);                    // hardest relevant item: the last (largest) position
+        sh = (G_total - (int64_t)nj) < max_rank ? 1 : 0;
+      }
+      const int64_t gq = pv.q_base + q;
+      ap[gq] = a; inp[gq] = np; first[gq] = f; is_short[gq] = sh;
+    }
+    if (!reduce_now) return;
+  } else if (q < Q) {
+    query_metrics(counts, q, G_total, stride, max_rank, ap, first, is_short, inp);
+  }
+  if (!last_cta_done(ticket)) return;
+  reduce_body(rs_raw, ap, first, is_short, Qred, max_rank, ties, cmc, summary, inp, overflow, pv, stats_out);
+}
+
+// Peer exchange, last stage of a query block (see rank_metrics_kernel).  cmc / summary / stats_out are written when
+// the block is the last one of the evaluation (q_base + Qb == Qtot).
+int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
+                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream) {
+  IEEE_REQUIRE(peers && peers->shards >= 1 && local_stats, "rank_metrics_peer: needs a peer exchange");
+  IEEE_REQUIRE(max_rank >= 1 && max_rank <= 8192, "rank_metrics_peer: bad shape (max_rank=%d)", max_rank);
+  if (max_rank > G_total) max_rank = (int32_t)G_total;
+  const PeerView& v = *peers;
+  const int last = (v.q_base + v.Qb == Qtot) ? 1 : 0;
+  IEEE_REQUIRE(!last || (cmc && summary), "rank_metrics_peer: the last block needs the result buffers");
+  uint8_t* mine = v.base[v.my];
+  const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
+  IEEE_ENSURE_DYN_SMEM(rank_metrics_kernel, smem);
+  rank_metrics_kernel<<<(unsigned)((v.Qb + 1023) / 1024), 1024, smem, stream>>>(
+      nullptr, v.Qb, G_total, v.W + 2, max_rank, reinterpret_cast<double*>(mine + v.off_ap),
+      reinterpret_cast<int32_t*>(mine + v.off_first), reinterpret_cast<int32_t*>(mine + v.off_short),
+      reinterpret_cast<double*>(mine + v.off_inp), nullptr, cmc, summary, nullptr,
+      reinterpret_cast<uint32_t*>(mine + kPeerTicketOffset), v, local_stats, stats_out, last, Qtot);
+  count_launch(1, "rank_metrics_kernel (peer)");
+  IEEE_CUDA_CHECK(cudaGetLastError());
+  return IEEE_OK;
+}
+
 size_t rank_finalize_workspace_bytes(int64_t Q) { return 2 * align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4); }
 
 int rank_query_metrics(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
@@ -1135,7 +1199,7 @@ int rank_reduce(const double* ap, const int32_t* first, const int32_t* short_lis
 int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t shards, int32_t cap,
                   int32_t max_rank, const unsigned long long* ties, float* cmc, ieee_eval_summary* summary,
                   double* per_query_ap, int32_t* per_query_first, void* workspace, cudaStream_t stream,
-                  const int32_t* overflow) {
+                  const int32_t* overflow, uint32_t* ticket) {
   IEEE_REQUIRE(workspace != nullptr, "rank_finalize: null workspace");
   if (max_rank > G_total) max_rank = (int32_t)G_total;   // rank.py:110-115
   uint8_t* w = static_cast<uint8_t*>(workspace);
@@ -1143,6 +1207,18 @@ int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t sha
   int32_t* first = per_query_first ? per_query_first : reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8));
   int32_t* is_short = reinterpret_cast<int32_t*>(w + align256(size_t(Q) * 8) + align256(size_t(Q) * 4));
   double* inp = reinterpret_cast<double*>(w + align256(size_t(Q) * 8) + 2 * align256(size_t(Q) * 4));
+  if (ticket != nullptr) {       // a zeroed word is at hand: both stages in one launch
+    IEEE_REQUIRE(counts && cmc && summary, "rank_finalize: null pointer");
+    IEEE_REQUIRE(Q > 0 && G_total > 0 && max_rank >= 1 && max_rank <= 8192 && shards >= 1 && cap >= 1, "rank_finalize: bad shape");
+    const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
+    IEEE_ENSURE_DYN_SMEM(rank_metrics_kernel, smem);
+    rank_metrics_kernel<<<(unsigned)((Q + 1023) / 1024), 1024, smem, stream>>>(counts, Q, G_total, shards * cap + 2, max_rank, ap, first,
+                                                                                is_short, inp, ties, cmc, summary, overflow, ticket,
+                                                                                no_peers(), nullptr, nullptr, 1, Q);
+    count_launch(1, "rank_metrics_kernel");
+    IEEE_CUDA_CHECK(cudaGetLastError());
+    return IEEE_OK;
+  }
   int rc = rank_query_metrics(counts, Q, G_total, shards, cap, max_rank, ap, first, is_short, inp, stream);
   if (rc) return rc;
   return rank_reduce(ap, first, is_short, Q, max_rank, ties, cmc, summary, inp, overflow, stream, nullptr, nullptr);

@@ -374,8 +374,9 @@ class RetrievalEvaluator:
                               idx[s:e].data_ptr(), val[s:e].data_ptr(), _lib.stream())
         return idx, val
 
-    def _rank_block_peer(self, dist, qp, qc, link, Qb_max, Qtot, q_base, cap, W, stats):
-        """gather -> count -> owner metrics of one query block with the exchanges as stores into peer memory."""
+    def _rank_block_peer(self, dist, qp, qc, link, Qb_max, Qtot, q_base, cap, W, stats, cmc, summ, stats_out, k_eff):
+        """gather -> count -> metrics of one query block with the exchanges as stores into peer memory; the metrics
+        kernel of the last block also reduces over all queries."""
         Qb = dist.shape[0]
         ex = link.descriptor(Qb_max, Qb, Qtot, q_base, cap, W, link.next_epoch())
         junk = torch.empty((Qb, cap), dtype=torch.int64, device=self.device)
@@ -390,9 +391,10 @@ class RetrievalEvaluator:
         TRACE.mark("  gather (lists stored into every peer)")
         _lib.call("ieee_rank_count_peer", dist.data_ptr(), dist.stride(0), self.G, self.g_offset, n_rel.data_ptr(),
                   junk.data_ptr(), n_junk.data_ptr(), stats.data_ptr(), C.byref(ex), st)
-        TRACE.mark("  count (partial counts stored into the owners)")
-        _lib.call("ieee_rank_owner_metrics_peer", self.g_total, self.max_rank, stats.data_ptr(), C.byref(ex), st)
-        TRACE.mark("  owner metrics (results stored into every peer)")
+        TRACE.mark("  count (partial counts stored into every peer)")
+        _lib.call("ieee_rank_metrics_peer", self.g_total, k_eff, stats.data_ptr(), cmc.data_ptr(), summ.data_ptr(),
+                  stats_out.data_ptr(), C.byref(ex), st)
+        TRACE.mark("  metrics (+ reduction on the last block)")
         return ex
 
     def _rank_block(self, dist, qp, qc, cap, width, ap, first, short, ties, inp):
@@ -747,12 +749,10 @@ class RetrievalEvaluator:
                     e = min(Q, s + rows)
                     if s > 0:
                         dist = contraction(s, e)
-                    ex = self._rank_block_peer(dist, qp[s:e], qc[s:e], link, rows, Q, s, cap, W, stats)
+                    ex = self._rank_block_peer(dist, qp[s:e], qc[s:e], link, rows, Q, s, cap, W, stats, cmc, summ, ties, k_eff)
                     if return_distmat:
                         full = dist.clone() if full is None else torch.cat([full, dist], 0)
                 TRACE.mark("rank stages done")
-                _lib.call("ieee_rank_reduce_peer", k_eff, cmc.data_ptr(), summ.data_ptr(), ties.data_ptr(), C.byref(ex),
-                          _lib.stream())
                 offs = [lib.ieee_peer_result_offset(i, rows, Q, cap, W, self.world) for i in (0, 1)]
                 ap = link.view[offs[0]: offs[0] + 8 * Q].view(torch.float64)       # every rank holds all per-query results
                 first = link.view[offs[1]: offs[1] + 4 * Q].view(torch.int32)

@@ -353,22 +353,26 @@ int ieee_gnn_rerank(const float* neg_score, int64_t lds, int64_t N, int32_t k1, 
 
 /* ------------------------------------------------------------------------------------------------
  * Peer exchange: the two exchange steps of a gallery sharded over the GPUs of one box (relevant lists to every rank,
- * partial counts back) as STORES into NVLink peer memory from inside the rank kernels, with flag words for the
- * hand-over -- no collective launches between the kernels of a step.
+ * partial counts to every rank) as STORES into NVLink peer memory from inside the rank kernels, with flag words for
+ * the hand-over -- no collective launches between the kernels of a step.
  *
  * Every rank allocates one exchange buffer (ieee_peer_alloc: cudaMalloc, zeroed, plus its 64-byte cudaIpc handle),
  * the handles are exchanged once through the host (any process group), every rank maps its peers' buffers
  * (ieee_peer_open).  Per query block all ranks then call, with identical Qb / cap / W / epoch and their own my_shard:
  *
- *   ieee_rank_gather_peer         lists of this shard -> slot my_shard of EVERY rank's list table
- *   ieee_rank_count_peer          waits for all lists; streams the local rows; partial counts -> the OWNER of each query
- *                                 (queries of a block are owned in contiguous slices of ceil(Qb / shards))
- *   ieee_rank_owner_metrics_peer  waits for all partial counts of the owned queries; sums them (integers: exact in any
- *                                 order); AP / first hit / mINP term -> EVERY rank's per-query result arrays
- * and once per evaluation
- *   ieee_rank_reduce_peer         waits for all results; the same fixed-tree reduction on every rank: bit-identical
- *                                 (cmc, summary) everywhere; stats_out (int64[3], device, may be NULL) receives
- *                                 {list overflow (needed capacity or 0), tie pairs, longest merged list} over all shards.
+ *   ieee_rank_gather_peer    lists of this shard -> slot my_shard of EVERY rank's list table
+ *   ieee_rank_count_peer     waits for all lists; streams the local rows; partial counts -> slot my_shard of EVERY
+ *                            rank's count table
+ *   ieee_rank_metrics_peer   waits for all partial counts; sums them (integers: exact in any order); AP / first hit /
+ *                            mINP term of every query of the block into this rank's result arrays; on the LAST block
+ *                            of the evaluation (q_base + Qb == Qtot) the kernel's last CTA also runs the fixed-tree
+ *                            reduction over all Qtot queries: bit-identical (cmc, summary) on every rank without a
+ *                            result broadcast.  cmc / summary may be NULL for earlier blocks.  stats_out (int64[3],
+ *                            device, may be NULL) receives {list overflow (needed capacity or 0), tie pairs, longest
+ *                            merged list} over all shards.
+ * Two hand-overs per block suffice (a first version had a third, owner -> everybody): seeing a peer's count flag of block n
+ * says its count kernel is done with the lists, seeing its list flag of block n + 1 says its metrics kernel is done
+ * with the count rows, so the next block may overwrite both.
  * A kernel that waits spins on flags in its OWN buffer (bounded: it traps after ~4 s); it never waits for a kernel of
  * the same rank that is queued behind it, so the ranks cannot deadlock as long as all of them issue the same calls.
  * `epoch` must grow by one per query block (never reuse a value with the same buffers).
@@ -396,14 +400,13 @@ int ieee_rank_gather_peer(const float* distmat, int64_t ld, int64_t G, const int
 int ieee_rank_count_peer(const float* distmat, int64_t ld, int64_t G, int64_t g_offset, const int32_t* n_rel,
                          const uint64_t* junk, const int32_t* n_junk, unsigned long long* stats,
                          const ieee_peer_exchange* ex, ieee_stream_t stream);
-int ieee_rank_owner_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats,
-                                 const ieee_peer_exchange* ex, ieee_stream_t stream);
-int ieee_rank_reduce_peer(int32_t max_rank, float* cmc, ieee_eval_summary* summary, int64_t* stats_out,
-                          const ieee_peer_exchange* ex, ieee_stream_t stream);
+int ieee_rank_metrics_peer(int64_t G_total, int32_t max_rank, const unsigned long long* stats, float* cmc,
+                           ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
+                           ieee_stream_t stream);
 /* One query block of a sharded evaluation in ONE call (the sharded counterpart of ieee_retrieve_eval_prepared): pack the
- * queries -> contraction against this rank's packed gallery slice -> gather / count / owner metrics / reduce with the
- * peer exchange.  `ex` describes one block of Q rows (Qb == Qtot == Q, q_base == 0) with the list capacity and row width
- * every rank agreed on; G_total / g_offset place the slice in the whole gallery.  stats_out as in ieee_rank_reduce_peer:
+ * queries -> contraction against this rank's packed gallery slice -> gather / count / metrics with the peer
+ * exchange.  `ex` describes one block of Q rows (Qb == Qtot == Q, q_base == 0) with the list capacity and row width
+ * every rank agreed on; G_total / g_offset place the slice in the whole gallery.  stats_out as in ieee_rank_metrics_peer:
  * stats_out[0] != 0 or stats_out[2] > ex->W mean the sizes were too small and the call must be repeated with larger ones. */
 size_t ieee_retrieve_prepared_peer_workspace_bytes(int64_t Q, int64_t D, int precision, int32_t cap);
 int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int64_t Q, int64_t D, int metric, int normalize,

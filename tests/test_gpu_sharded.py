@@ -87,7 +87,7 @@ def test_topk_merge_across_shards():
 def test_peer_exchange_protocol_on_one_gpu(shards):
     """The peer-memory exchange (ieee_rank_*_peer) with `shards` virtual ranks on ONE device: one buffer and one stream
     per virtual rank, kernels of different ranks handing over through the flag words exactly as they do across GPUs.
-    Two query blocks of different size, so that epochs, block offsets and owner slices are all exercised."""
+    Two query blocks of different size, so that epochs, block offsets and the count-table slots are all exercised."""
     import ctypes as C
     from ieee_b200.peer import LocalPeers
     s = make_retrieval_set(150, 1203, 20, 4, dim=64, sigma=2.0, seed=40 + shards)
@@ -111,6 +111,8 @@ def test_peer_exchange_protocol_on_one_gpu(shards):
     streams = [torch.cuda.Stream() for _ in range(shards)]
     stats = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(shards)]
     keep = []
+    results = [(torch.empty(20, dtype=torch.float32, device=dev), torch.empty(64, dtype=torch.uint8, device=dev),
+                torch.zeros(4, dtype=torch.int64, device=dev)) for _ in range(shards)]
     torch.cuda.synchronize()
     epoch = 0
     for q0 in range(0, Q, Qb_max):
@@ -130,17 +132,10 @@ def test_peer_exchange_protocol_on_one_gpu(shards):
                           stats[r].data_ptr(), C.byref(ex), st)
                 _lib.call("ieee_rank_count_peer", blk.data_ptr(), blk.stride(0), g1 - g0, g0, n_rel.data_ptr(), junk.data_ptr(),
                           n_junk.data_ptr(), stats[r].data_ptr(), C.byref(ex), st)
-                _lib.call("ieee_rank_owner_metrics_peer", G, 20, stats[r].data_ptr(), C.byref(ex), st)
-    results = []
-    for r in range(shards):
-        ex = peers.descriptor(r, Qb_max, Q - (Q - 1) // Qb_max * Qb_max, Q, (Q - 1) // Qb_max * Qb_max, cap, W, epoch)
-        cmc = torch.empty(20, dtype=torch.float32, device=dev)
-        summ = torch.empty(64, dtype=torch.uint8, device=dev)
-        st_out = torch.zeros(4, dtype=torch.int64, device=dev)
-        with torch.cuda.stream(streams[r]):
-            _lib.call("ieee_rank_reduce_peer", 20, cmc.data_ptr(), summ.data_ptr(), st_out.data_ptr(), C.byref(ex),
-                      streams[r].cuda_stream)
-        results.append((cmc, summ, st_out))
+                # the metrics kernel of the last block also reduces over all Q queries
+                cmc, summ, st_out = results[r]
+                _lib.call("ieee_rank_metrics_peer", G, 20, stats[r].data_ptr(), cmc.data_ptr(), summ.data_ptr(),
+                          st_out.data_ptr(), C.byref(ex), st)
     torch.cuda.synchronize()
     off_ap, off_first = (lib.ieee_peer_result_offset(i, Qb_max, Q, cap, W, shards) for i in (0, 1))
     ap_o = np.array([((np.arange(p.size) + 1.0) / (p + 1.0)).sum() / p.size if p.size else 0.0 for p in pos])
