@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libieee_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_VALID_QUERY, ERR_SHORT_RANK_LIST, ERR_CAPACITY = range(7)
 METRICS = {"euclidean": 0, "cosine": 1}
+PREPARE_DEFER_JOIN, PREPARE_KEEP_CENTER = 1, 2      # flags of ieee_gallery_prepare
 INTERNAL_METRICS = {"neg_dot": 2}          # -(a . b): GNN re-ranking (not a torchreid metric name)
 PRECISIONS = {"f16x3": 0, "bf16": 1, "fp32_simt": 2}
 DTYPES = {torch.float32: 0, torch.bfloat16: 1}
@@ -60,14 +61,16 @@ SIGNATURES = {
     "ieee_eval_workspace_bytes": (sz, [i64, i64, i32]),
     "ieee_eval_market1501": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
     "ieee_gallery_prepare_workspace_bytes": (sz, [i64]),
-    "ieee_gallery_prepare": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, i64, vp, vp, vp, vp, vp]),
+    "ieee_gallery_prepare": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, i64, i64, vp, vp, vp, vp, C.c_int,
+                                       vp, vp]),
+    "ieee_gallery_group_join": (C.c_int, [vp]),
     "ieee_eval_market1501_f64": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
     "ieee_retrieve_workspace_bytes": (sz, [i64, i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval": (C.c_int, [vp, i64, vp, i64, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, i32, i32,
                                      C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "ieee_retrieve_prepared_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval_prepared": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, i32, i32,
-                                              C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, sz, vp]),
+                                              C.POINTER(i32), vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
     "ieee_retrieve_fused_workspace_bytes": (sz, [i64, i64, i64]),
     "ieee_retrieve_fused_spill_capacity": (C.c_uint32, [i64, i64]),
     "ieee_retrieve_eval_fused_prepared": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, i32,
@@ -102,7 +105,7 @@ SIGNATURES.update({
     "ieee_peer_result_offset": (sz, [C.c_int, i64, i64, i32, i32, i32]),
     "ieee_retrieve_prepared_peer_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval_prepared_peer": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, i64, i64,
-                                                   vp, vp, vp, i32, vp, i64, vp, vp, vp, _PEER, vp, sz, vp]),
+                                                   vp, vp, vp, i32, vp, i64, vp, vp, vp, _PEER, vp, vp, sz, vp]),
 })
 
 _lib = None

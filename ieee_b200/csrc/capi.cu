@@ -162,11 +162,28 @@ static int side_lane(SideLane** out) {
   std::lock_guard<std::mutex> lock(g_side_mutex);
   SideLane& l = g_side[dev];
   if (l.stream == nullptr) {
-    IEEE_CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    // highest priority: the lane's tiny label-only kernels get the SM slots the bandwidth-bound kernel beside them
+    // frees, instead of queueing behind its remaining waves
+    int lo = 0, hi = 0;
+    IEEE_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    IEEE_CUDA_CHECK(cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, hi));
     IEEE_CUDA_CHECK(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
     IEEE_CUDA_CHECK(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
   }
   *out = &l;
+  return IEEE_OK;
+}
+// `stream` waits for whatever the side lane of the current device was last given (nothing, if it was never used)
+static int side_lane_join(cudaStream_t stream) {
+  int dev = 0;
+  IEEE_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return IEEE_OK;
+  cudaEvent_t join = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    join = g_side[dev].join;
+  }
+  if (join != nullptr) IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
   return IEEE_OK;
 }
 }  // namespace ieee
@@ -465,14 +482,16 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
 size_t ieee_gallery_prepare_workspace_bytes(int64_t D) { return D > 0 ? feature_center_workspace_bytes(D) : 0; }
 
 int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int64_t D, int metric, int normalize, int precision,
-                         const int64_t* g_pids, const void* center_src, int64_t ld_src, int64_t rows_src, float* center,
-                         void* g_packed, void* group, void* workspace, ieee_stream_t stream_) {
+                         const int64_t* g_pids, const void* q, int64_t ldq, int64_t Q, float* center, void* g_packed,
+                         void* group, void* q_packed, int flags, void* workspace, ieee_stream_t stream_) {
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   IEEE_REQUIRE(gf && g_packed && G > 0 && D > 0, "gallery_prepare: bad arguments (G=%lld D=%lld)", (long long)G, (long long)D);
-  IEEE_REQUIRE(center_src == nullptr || (center != nullptr && workspace != nullptr && rows_src > 0),
-               "gallery_prepare: a centre source needs the centre buffer and the workspace");
+  const bool new_center = q != nullptr && !(flags & IEEE_PREPARE_KEEP_CENTER);
+  IEEE_REQUIRE(!new_center || (center != nullptr && workspace != nullptr && Q > 0),
+               "gallery_prepare: a centre from the query rows needs the centre buffer and the workspace");
+  IEEE_REQUIRE(q_packed == nullptr || (q != nullptr && Q > 0), "gallery_prepare: packing the queries needs the query rows");
   tl_enter(stream, "enter gallery_prepare");
   SideLane* lane = nullptr;
   const bool grouping = g_pids != nullptr && group != nullptr;
@@ -481,19 +500,29 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
     IEEE_CUDA_CHECK(cudaEventRecord(lane->fork, stream));
   }
   // the bandwidth-bound kernels are issued FIRST: the six API calls of the side lane took ~25 us of host time during
-  // which the GPU had nothing to do (profiles/r2_step_marks.txt)
-  if (center_src != nullptr &&
-      (rc = feature_center(center_src, dtype, ld_src, rows_src, D, normalize, 0, center, workspace, stream)))
-    return rc;
+  // which the GPU had nothing to do (profiles/r2_step_marks_n1_before.txt)
+  if (new_center && (rc = feature_center(q, dtype, ldq, Q, D, normalize, 0, center, workspace, stream))) return rc;
   if ((rc = pack_features(gf, dtype, ldg, G, D, metric, normalize, precision, center, g_packed, stream))) return rc;
+  // the query block too, when asked: the caller's host work between this call and the evaluation call then hides
+  // behind it (with a small gallery shard the gallery pack alone is over before the next call arrives)
+  if (q_packed != nullptr && (rc = pack_features(q, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream)))
+    return rc;
   if (grouping) {
     IEEE_CUDA_CHECK(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
     if ((rc = gallery_group(g_pids, G, group, lane->stream))) return rc;
     IEEE_CUDA_CHECK(cudaEventRecord(lane->join, lane->stream));
-    IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
-    count_launch(0, "join grouping (side stream)");
+    if (!(flags & IEEE_PREPARE_DEFER_JOIN)) {
+      IEEE_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
+      count_launch(0, "join grouping (side stream)");
+    }
   }
   return IEEE_OK;
+}
+
+int ieee_gallery_group_join(ieee_stream_t stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  return side_lane_join((cudaStream_t)stream);
 }
 
 // float64 distance matrix: ranked in float64 order (rank.py:117 argsorts whatever dtype it is given)
@@ -563,25 +592,33 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
                                 const int64_t* q_pids,
                                 const int64_t* q_camids, const int64_t* g_camids, int32_t max_rank, int32_t cap,
                                 int32_t* cap_host_out, float* distmat, int64_t ld, float* cmc, ieee_eval_summary* summary,
-                                double* per_query_ap, int32_t* per_query_first, void* workspace, size_t workspace_bytes,
-                                ieee_stream_t stream_) {
+                                double* per_query_ap, int32_t* per_query_first, const void* q_packed_ready,
+                                void* workspace, size_t workspace_bytes, ieee_stream_t stream_) {
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  IEEE_REQUIRE(qf && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace,
+  IEEE_REQUIRE((qf || q_packed_ready) && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace,
                "retrieve: null pointer");
   IEEE_REQUIRE(Q > 0 && G > 0 && D > 0 && ld >= G && max_rank >= 1, "retrieve: bad shape Q=%lld G=%lld D=%lld ld=%lld max_rank=%d",
                (long long)Q, (long long)G, (long long)D, (long long)ld, max_rank);
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve: workspace must be 256-byte aligned");
   Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
-  void* q_packed = a.take(ieee_packed_bytes(Q, D, precision));
-  int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64)
-  void* fix = a.take(distmat_fixup_bytes(Q));
+  int32_t* scratch = static_cast<int32_t*>(a.take(256));   // [0] cap, [1] overflow, [2..3] ties (u64), [8] metrics ticket
+  void* fix = a.take(distmat_fixup_bytes(Q));              // (directly behind the scratch words: one clear covers both)
+  const void* q_packed = q_packed_ready;
+  if (q_packed == nullptr) q_packed = a.take(ieee_packed_bytes(Q, D, precision));
   if (!q_packed || !scratch || !fix) { set_error("retrieve: workspace too small"); return IEEE_ERR_WORKSPACE; }
   tl_enter(stream, "enter retrieve_eval_prepared");
-  // the query pack's first CTA clears the scratch words and the fix-up list header for the kernels behind it
-  const ZeroJob zero{{reinterpret_cast<uint32_t*>(scratch), static_cast<uint32_t*>(fix)}, {64, 2}};
-  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream, &zero))) return rc;
+  if (q_packed_ready != nullptr) {
+    // queries packed by ieee_gallery_prepare: clear the scratch words and the fix-up list header in one node
+    IEEE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 256 + 8, stream));
+    count_launch(0, "memset scratch + fix list");
+  } else {
+    // the query pack's first CTA clears the scratch words and the fix-up list header for the kernels behind it
+    const ZeroJob zero{{reinterpret_cast<uint32_t*>(scratch), static_cast<uint32_t*>(fix)}, {64, 2}};
+    if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, const_cast<void*>(q_packed), stream, &zero)))
+      return rc;
+  }
   if (cap <= 0) {
     int32_t need = 0;
     if ((rc = ieee_rank_list_cap_sync(group, G, q_pids, Q, scratch, &need, stream_))) return rc;
@@ -601,6 +638,7 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
   }
   if ((rc = distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_, true))) return rc;
   unsigned long long* ties = reinterpret_cast<unsigned long long*>(scratch + 2);
+  if ((rc = side_lane_join(stream))) return rc;      // a grouping ieee_gallery_prepare left on the side lane
   if ((rc = rank_gather(distmat, ld, Q, G, q_pids, q_camids, g_camids, group, 0, cap, rel, n_rel, junk, n_junk, scratch + 1, stream))) return rc;
   if ((rc = rank_count(distmat, ld, Q, G, 0, 1, cap, 0, rel, n_rel, junk, n_junk, counts, ties, stream))) return rc;
   // scratch: [0] cap, [1] overflow, [2..3] ties, [8] ticket of the metrics kernel (all cleared by the query pack)
@@ -616,7 +654,6 @@ int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg,
                        ieee_stream_t stream_) {
   int rc = check_device();
   if (rc) return rc;
-  cudaStream_t stream = (cudaStream_t)stream_;
   IEEE_REQUIRE(gf && g_pids && workspace, "retrieve: null pointer");
   IEEE_REQUIRE(Q > 0 && G > 0 && D > 0, "retrieve: bad shape Q=%lld G=%lld D=%lld", (long long)Q, (long long)G, (long long)D);
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve: workspace must be 256-byte aligned");
@@ -630,13 +667,15 @@ int ieee_retrieve_eval(const void* qf, int64_t ldq, const void* gf, int64_t ldg,
   const bool centred = auto_center(metric, precision);
   IEEE_REQUIRE(qf != nullptr, "retrieve: null pointer");
   if (!centred) center = nullptr;
+  // the evaluation call packs the queries itself (its workspace holds them) and joins the side lane before the gather
   if ((rc = ieee_gallery_prepare(gf, ldg, dtype, G, D, metric, normalize, precision, g_pids, centred ? qf : nullptr, ldq, Q,
-                                 center, g_packed, group, cws, stream_)))
+                                 center, g_packed, group, nullptr, IEEE_PREPARE_DEFER_JOIN, cws, stream_)))
     return rc;
   const size_t used = align256(a.off);
   return ieee_retrieve_eval_prepared(qf, ldq, dtype, Q, D, metric, normalize, precision, g_packed, group, center, G, q_pids, q_camids,
                                      g_camids, max_rank, cap, cap_host_out, distmat, ld, cmc, summary, per_query_ap,
-                                     per_query_first, static_cast<uint8_t*>(workspace) + used, workspace_bytes - used, stream_);
+                                     per_query_first, nullptr, static_cast<uint8_t*>(workspace) + used, workspace_bytes - used,
+                                     stream_);
 }
 
 int ieee_topk(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, const int64_t* q_pids,
@@ -836,11 +875,12 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
                                      int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
                                      const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
                                      ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
-                                     void* workspace, size_t workspace_bytes, ieee_stream_t stream_) {
+                                     const void* q_packed_ready, void* workspace, size_t workspace_bytes,
+                                     ieee_stream_t stream_) {
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  IEEE_REQUIRE(qf && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace && ex,
+  IEEE_REQUIRE((qf || q_packed_ready) && g_packed && group && q_pids && q_camids && g_camids && distmat && cmc && summary && workspace && ex,
                "retrieve (peer): null pointer");
   IEEE_REQUIRE(Q > 0 && G > 0 && D > 0 && ld >= G && max_rank >= 1 && G_total >= G && g_offset >= 0,
                "retrieve (peer): bad shape Q=%lld G=%lld D=%lld ld=%lld", (long long)Q, (long long)G, (long long)D, (long long)ld);
@@ -848,21 +888,29 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
   IEEE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "retrieve (peer): workspace must be 256-byte aligned");
   const int32_t cap = ex->cap;
   Arena a{static_cast<uint8_t*>(workspace), workspace_bytes, 0};
-  void* q_packed = a.take(ieee_packed_bytes(Q, D, precision));
-  void* fix = a.take(distmat_fixup_bytes(Q));
+  unsigned long long* stats = static_cast<unsigned long long*>(a.take(256));   // this rank's own statistics
+  void* fix = a.take(distmat_fixup_bytes(Q));                                   // (directly behind them: one clear covers both)
+  const void* q_packed = q_packed_ready;
+  if (q_packed == nullptr) q_packed = a.take(ieee_packed_bytes(Q, D, precision));
   uint64_t* junk = static_cast<uint64_t*>(a.take(size_t(Q) * cap * 8));
   int32_t* n_rel = static_cast<int32_t*>(a.take(size_t(Q) * 4));
   int32_t* n_junk = static_cast<int32_t*>(a.take(size_t(Q) * 4));
-  unsigned long long* stats = static_cast<unsigned long long*>(a.take(256));   // this rank's own statistics
   if (!q_packed || !fix || !junk || !n_rel || !n_junk || !stats) {
     set_error("retrieve (peer): workspace too small (%zu bytes given, need %zu for cap=%d)", workspace_bytes,
               ieee_retrieve_prepared_peer_workspace_bytes(Q, D, precision, cap), cap);
     return IEEE_ERR_WORKSPACE;
   }
   tl_enter(stream, "enter retrieve_eval_prepared_peer");
-  const ZeroJob zero{{reinterpret_cast<uint32_t*>(stats), static_cast<uint32_t*>(fix)}, {64, 2}};
-  if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, q_packed, stream, &zero))) return rc;
+  if (q_packed_ready != nullptr) {
+    IEEE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 256 + 8, stream));
+    count_launch(0, "memset stats + fix list");
+  } else {
+    const ZeroJob zero{{reinterpret_cast<uint32_t*>(stats), static_cast<uint32_t*>(fix)}, {64, 2}};
+    if ((rc = pack_features(qf, dtype, ldq, Q, D, metric, normalize, precision, center, const_cast<void*>(q_packed), stream, &zero)))
+      return rc;
+  }
   if ((rc = distmat_packed(q_packed, Q, g_packed, G, D, metric, precision, distmat, ld, fix, stream_, true))) return rc;
+  if ((rc = side_lane_join(stream))) return rc;      // a grouping ieee_gallery_prepare left on the side lane
   if ((rc = ieee_rank_gather_peer(distmat, ld, G, q_pids, q_camids, g_camids, group, g_offset, n_rel, junk, n_junk, stats, ex,
                                   stream_)))
     return rc;

@@ -1111,36 +1111,48 @@ __global__ void __launch_bounds__(1024) rank_metrics_kernel(const int32_t* __res
                                                              const PeerView pv, const unsigned long long* local_stats,
                                                              long long* stats_out, int reduce_now, int64_t Qred) {
   extern __shared__ __align__(16) uint8_t rs_raw[];
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pv.shards) {
-    peer_signal_and_wait(pv, 1, local_stats);       // every shard's partial counts (and statistics) have landed here
-    if (q < Q) {
-      const int32_t* part = reinterpret_cast<const int32_t*>(pv.base[pv.my] + pv.off_cnt) + q * stride;
-      const int64_t shard_stride = (int64_t)pv.Qb * stride;
-      int R = 0, nj = 0;
-      for (int s = 0; s < pv.shards; ++s) { R += part[s * shard_stride + stride - 2]; nj += part[s * shard_stride + stride - 1]; }
-      double a = 0.0, np = 0.0;
-      int32_t f = -1, sh = 0;
-      if (R > 0 && R <= pv.W) {                       // (R > W: rows too narrow, flagged through the statistics; rerun)
-        double acc = 0.0;
+  // one WARP per query: lane k owns the k-th relevant item (its summed position and its term of the AP sum -- the
+  // division is the expensive part), then every lane adds the terms in k order: the same sequence of fp64 additions
+  // as the one-thread-per-query loop of rank_query_kernel, hence the same bits
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pv.shards) peer_signal_and_wait(pv, 1, local_stats);       // every shard's partial counts (and statistics) have landed here
+  if (q < Q) {
+    const int shards = pv.shards ? pv.shards : 1;
+    const int32_t* part = pv.shards ? reinterpret_cast<const int32_t*>(pv.base[pv.my] + pv.off_cnt) + q * stride : counts + q * stride;
+    const int64_t shard_stride = (int64_t)pv.Qb * stride;
+    int R = 0, nj = 0;
+    if (lane < shards) { R = part[lane * shard_stride + stride - 2]; nj = part[lane * shard_stride + stride - 1]; }
+    for (int o = 16; o > 0; o >>= 1) { R += __shfl_xor_sync(0xffffffffu, R, o); nj += __shfl_xor_sync(0xffffffffu, nj, o); }
+    double a = 0.0, np = 0.0;
+    int32_t f = -1, sh = 0;
+    const int width = stride - 2;
+    if (R > 0 && R <= width) {                        // (R > width: rows too narrow, flagged through the statistics; rerun)
+      double acc = 0.0;
+      int last_pos = 0;
+      for (int base = 0; base < R; base += 32) {
+        const int k = base + lane;
         int pos = 0;
-        for (int k = 0; k < R; ++k) {
-          pos = 0;
-          for (int s = 0; s < pv.shards; ++s) pos += part[s * shard_stride + k];
-          if (k == 0) f = pos;
-          acc += (double)(k + 1) / ((double)pos + 1.0);          // rank.py:155-160
-        }
-        a = acc / (double)R;
-        np = (double)R / ((double)pos + 1.0);                    // hardest relevant item: the last (largest) position
-        sh = (G_total - (int64_t)nj) < max_rank ? 1 : 0;
+        if (k < R)
+          for (int s = 0; s < shards; ++s) pos += part[s * shard_stride + k];
+        const double term = k < R ? (double)(k + 1) / ((double)pos + 1.0) : 0.0;          // rank.py:155-160
+        const int n = min(32, R - base);
+        for (int j = 0; j < n; ++j) acc += __shfl_sync(0xffffffffu, term, j);
+        if (base == 0) f = __shfl_sync(0xffffffffu, pos, 0);
+        last_pos = __shfl_sync(0xffffffffu, pos, n - 1);
       }
-      const int64_t gq = pv.q_base + q;
-      ap[gq] = a; inp[gq] = np; first[gq] = f; is_short[gq] = sh;
+      a = acc / (double)R;
+      // inverse negative penalty (README.rst:45, Ye et al. TPAMI 2021): R / (1-based rank of the hardest relevant item)
+      np = (double)R / ((double)last_pos + 1.0);
+      sh = (G_total - (int64_t)nj) < max_rank ? 1 : 0;
     }
-    if (!reduce_now) return;
-  } else if (q < Q) {
-    query_metrics(counts, q, G_total, stride, max_rank, ap, first, is_short, inp);
+    if (lane == 0) {
+      const int64_t gq = pv.q_base + q;
+      ap[gq] = a; first[gq] = f; is_short[gq] = sh;
+      if (inp) inp[gq] = np;
+    }
   }
+  if (!reduce_now) return;
   if (!last_cta_done(ticket)) return;
   reduce_body(rs_raw, ap, first, is_short, Qred, max_rank, ties, cmc, summary, inp, overflow, pv, stats_out);
 }
@@ -1158,7 +1170,7 @@ int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, 
   uint8_t* mine = v.base[v.my];
   const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
   IEEE_ENSURE_DYN_SMEM(rank_metrics_kernel, smem);
-  rank_metrics_kernel<<<(unsigned)((v.Qb + 1023) / 1024), 1024, smem, stream>>>(
+  rank_metrics_kernel<<<(unsigned)((v.Qb + 31) / 32), 1024, smem, stream>>>(
       nullptr, v.Qb, G_total, v.W + 2, max_rank, reinterpret_cast<double*>(mine + v.off_ap),
       reinterpret_cast<int32_t*>(mine + v.off_first), reinterpret_cast<int32_t*>(mine + v.off_short),
       reinterpret_cast<double*>(mine + v.off_inp), nullptr, cmc, summary, nullptr,
@@ -1212,7 +1224,7 @@ int rank_finalize(const int32_t* counts, int64_t Q, int64_t G_total, int32_t sha
     IEEE_REQUIRE(Q > 0 && G_total > 0 && max_rank >= 1 && max_rank <= 8192 && shards >= 1 && cap >= 1, "rank_finalize: bad shape");
     const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
     IEEE_ENSURE_DYN_SMEM(rank_metrics_kernel, smem);
-    rank_metrics_kernel<<<(unsigned)((Q + 1023) / 1024), 1024, smem, stream>>>(counts, Q, G_total, shards * cap + 2, max_rank, ap, first,
+    rank_metrics_kernel<<<(unsigned)((Q + 31) / 32), 1024, smem, stream>>>(counts, Q, G_total, shards * cap + 2, max_rank, ap, first,
                                                                                 is_short, inp, ties, cmc, summary, overflow, ticket,
                                                                                 no_peers(), nullptr, nullptr, 1, Q);
     count_launch(1, "rank_metrics_kernel");

@@ -124,6 +124,10 @@ def _fused_buffers(Q, D, precision, cap, k_eff, device):
     return buf
 
 
+def _features_key(t: torch.Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape), t.stride(0), t.dtype)
+
+
 def _tensor_key(t):
     return (t.data_ptr(), t.numel(), t._version, str(t.device)) if isinstance(t, torch.Tensor) else None
 
@@ -260,6 +264,7 @@ class RetrievalEvaluator:
         self.G = self.labels.G
         self.g_total = self.G if g_total is None else g_total
         self._block = None
+        self._early_q = None
         self._copy = None
         self._host_gallery = None
         self._label_keys = (_tensor_key(g_pids), _tensor_key(g_camids))
@@ -268,7 +273,10 @@ class RetrievalEvaluator:
         self.fused_stats = None
 
     def _prepare_gallery(self, qf_dev):
-        """ieee_gallery_prepare: grouping + [centre from the query rows] + packing of a device-resident gallery."""
+        """ieee_gallery_prepare: grouping + [centre from the query rows] + packing of a device-resident gallery -- and
+        of the query rows themselves when they make one block: the host work between this call and the evaluation call
+        then hides behind that kernel (a small gallery shard alone is packed before the next call arrives).  The
+        grouping stays on the library's side stream until a consumer joins it (GalleryLabels.wait)."""
         gf = self._gallery_dev
         if gf.stride(1) != 1:
             gf = self._gallery_dev = gf.contiguous()
@@ -278,20 +286,38 @@ class RetrievalEvaluator:
         pk = PackedFeatures.__new__(PackedFeatures)
         pk.rows, pk.D, pk.metric, pk.precision = G, D, _lib.METRICS[self.metric], prec
         pk.buf = torch.empty(max(lib.ieee_packed_bytes(G, D, prec), 256), dtype=torch.uint8, device=self.device)
-        src = None
-        if self._use_center and self.center is None:
+        src, ws, qpk, flags = None, None, None, _lib.PREPARE_DEFER_JOIN
+        if qf_dev is not None and qf_dev.shape[0] > 0:
             src = qf_dev if qf_dev.stride(1) == 1 else qf_dev.contiguous()
             assert src.dtype == gf.dtype, "query and gallery features must have the same dtype"
+        if src is not None and self._use_center and self.center is None:
             self.center = torch.empty(D, dtype=torch.float32, device=self.device)
             ws = torch.empty(lib.ieee_gallery_prepare_workspace_bytes(D), dtype=torch.uint8, device=self.device)
-        pk.center = self.center
+        else:
+            flags |= _lib.PREPARE_KEEP_CENTER
+        center = self.center if self._use_center else None
+        pk.center = center
+        if src is not None and src.shape[0] <= self._block_rows_for(src.shape[0], G):
+            qpk = PackedFeatures.__new__(PackedFeatures)
+            qpk.rows, qpk.D, qpk.metric, qpk.precision, qpk.center = src.shape[0], D, pk.metric, prec, center
+            qpk.buf = torch.empty(max(lib.ieee_packed_bytes(src.shape[0], D, prec), 256), dtype=torch.uint8, device=self.device)
+            self._early_q = (_features_key(qf_dev), qpk)
         cur = torch.cuda.current_stream()
         _lib.call("ieee_gallery_prepare", gf.data_ptr(), gf.stride(0), _lib.DTYPES[gf.dtype], G, D, pk.metric, int(self.normalize),
                   prec, self.labels.pids.data_ptr(), _lib.ptr(src), src.stride(0) if src is not None else 0,
-                  src.shape[0] if src is not None else 0, _lib.ptr(self.center), pk.buf.data_ptr(),
-                  self.labels.group.data_ptr(), ws.data_ptr() if src is not None else None, cur.cuda_stream)
+                  src.shape[0] if src is not None else 0, _lib.ptr(center), pk.buf.data_ptr(),
+                  self.labels.group.data_ptr(), qpk.buf.data_ptr() if qpk is not None else None, flags, _lib.ptr(ws),
+                  cur.cuda_stream)
         self.labels.ready = cur.record_event()
+        self.labels.side_join = True
         self.chunks = [(0, pk)]
+
+    def _take_early_q(self, qf: torch.Tensor):
+        """The packed form of exactly these query rows, if _prepare_gallery made it (used once)."""
+        early, self._early_q = self._early_q, None
+        if early is not None and early[0] == _features_key(qf):
+            return early[1]
+        return None
 
     def _ensure_center(self, qf_dev: torch.Tensor):
         """Fix the centre (first query set seen) and prepare a device-resident gallery with it."""
@@ -301,9 +327,12 @@ class RetrievalEvaluator:
             self.center = feature_center(qf_dev, self.normalize)
 
     # -- one query block ---------------------------------------------------------------------------------
-    def _block_rows(self, Q: int) -> int:
-        rows = max(128, int(self.block_bytes // (4 * max(self.G, 1))) // 128 * 128)
+    def _block_rows_for(self, Q: int, G: int) -> int:
+        rows = max(128, int(self.block_bytes // (4 * max(G, 1))) // 128 * 128)
         return min(Q, rows)
+
+    def _block_rows(self, Q: int) -> int:
+        return self._block_rows_for(Q, self.G)
 
     def _ensure_block(self, rows: int):
         if self._block is None or self._block.shape[0] < rows:
@@ -354,7 +383,7 @@ class RetrievalEvaluator:
             qc = _as_device(q_camids, torch.int64, self.device) if masked else None
             rows = self._block_rows(Q)
             self._ensure_block(rows)
-            torch.cuda.current_stream().wait_event(self.labels.ready)
+            self.labels.wait(torch.cuda.current_stream())
             for s in range(0, Q, rows):
                 e = min(Q, s + rows)
                 dist = self._distance_block(PackedFeatures(qf[s:e], self.metric, self.normalize, self.precision, self.center))
@@ -383,7 +412,7 @@ class RetrievalEvaluator:
         n_rel = torch.empty(Qb, dtype=torch.int32, device=self.device)
         n_junk = torch.empty(Qb, dtype=torch.int32, device=self.device)
         cur = torch.cuda.current_stream()
-        cur.wait_event(self.labels.ready)
+        self.labels.wait(cur)
         st = cur.cuda_stream
         _lib.call("ieee_rank_gather_peer", dist.data_ptr(), dist.stride(0), self.G, qp.data_ptr(), qc.data_ptr(),
                   self.labels.camids.data_ptr(), self.labels.group.data_ptr(), self.g_offset, n_rel.data_ptr(), junk.data_ptr(),
@@ -400,7 +429,7 @@ class RetrievalEvaluator:
     def _rank_block(self, dist, qp, qc, cap, width, ap, first, short, ties, inp):
         Qb = dist.shape[0]
         st = _stages_for(Qb, cap, self.world, self.device, width)
-        torch.cuda.current_stream().wait_event(self.labels.ready)
+        self.labels.wait(torch.cuda.current_stream())
         st.gather(dist, qp, qc, self.labels, self.g_offset, stats=ties)     # kernels max / add straight into `ties`
         TRACE.mark("  gather")
         if self.world > 1:
@@ -473,7 +502,7 @@ class RetrievalEvaluator:
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             cur = torch.cuda.current_stream()
-            cur.wait_event(self.labels.ready)
+            self.labels.wait(cur)
             gpk = self.chunks[0][1]
             _lib.call("ieee_retrieve_eval_fused_prepared", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
                       _lib.METRICS[self.metric], int(self.normalize), gpk.buf.data_ptr(), self.labels.group.data_ptr(),
@@ -511,7 +540,7 @@ class RetrievalEvaluator:
                 memo_key = (self._label_keys, _tensor_key(q_pids), self.world)
             cap = _CAP_MEMO.get(memo_key, (0, 0))[0] if memo_key is not None else 0
             cur = torch.cuda.current_stream()
-            cur.wait_event(self.labels.ready)
+            self.labels.wait(cur, join=False)
             if cap <= 0:
                 # sizing pass: the capacity query synchronises once; later calls with the same labels skip it
                 cap = self.labels.list_cap(qp)
@@ -526,11 +555,13 @@ class RetrievalEvaluator:
             ap = torch.empty(Q, dtype=torch.float64, device=self.device)
             first = torch.empty(Q, dtype=torch.int32, device=self.device)
             gpk = self.chunks[0][1]
+            qpk = self._take_early_q(qf)          # packed already by ieee_gallery_prepare (first evaluation of this gallery)
             _lib.call("ieee_retrieve_eval_prepared", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
                       _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
                       _lib.ptr(self.center), self.G, qp.data_ptr(), qc.data_ptr(), self.labels.camids.data_ptr(), self.max_rank, cap, None,
                       self._block.data_ptr(), self._block.stride(0), res.data_ptr(), res.data_ptr() + res_off,
-                      ap.data_ptr(), first.data_ptr(), ws.data_ptr(), ws.numel(), cur.cuda_stream)
+                      ap.data_ptr(), first.data_ptr(), qpk.buf.data_ptr() if qpk is not None else None, ws.data_ptr(), ws.numel(),
+                      cur.cuda_stream)
             res_host.copy_(res, non_blocking=True)
             cur.synchronize()
             out = res_host.numpy()
@@ -573,14 +604,15 @@ class RetrievalEvaluator:
             ws, res, res_host = buf
             self._ensure_block(Q)
             cur = torch.cuda.current_stream()
-            cur.wait_event(self.labels.ready)
+            self.labels.wait(cur, join=False)
             gpk = self.chunks[0][1]
+            qpk = self._take_early_q(qf)
             _lib.call("ieee_retrieve_eval_prepared_peer", qf.data_ptr(), qf.stride(0), _lib.DTYPES[qf.dtype], Q, D,
                       _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
                       _lib.ptr(self.center), self.G, self.g_total, self.g_offset, qp.data_ptr(), qc.data_ptr(),
                       self.labels.camids.data_ptr(), self.max_rank, self._block.data_ptr(), self._block.stride(0),
-                      res.data_ptr() + 96, res.data_ptr() + 32, res.data_ptr(), C.byref(ex), ws.data_ptr(), ws.numel(),
-                      cur.cuda_stream)
+                      res.data_ptr() + 96, res.data_ptr() + 32, res.data_ptr(), C.byref(ex),
+                      qpk.buf.data_ptr() if qpk is not None else None, ws.data_ptr(), ws.numel(), cur.cuda_stream)
             res_host.copy_(res, non_blocking=True)
             cur.synchronize()
             out = res_host.numpy()
@@ -648,8 +680,11 @@ class RetrievalEvaluator:
             rows = self._block_rows(Q)
             # queries already in HBM: pack the first block before anything else, so the GPU is busy while the host
             # prepares the rest of the step
-            early_pack = (PackedFeatures(qf[: min(Q, rows)], self.metric, self.normalize, self.precision, self.center)
-                          if qf.is_cuda else None)
+            early_pack = None
+            if qf.is_cuda:
+                early_pack = self._take_early_q(qf) if rows >= Q else None
+                if early_pack is None:
+                    early_pack = PackedFeatures(qf[: min(Q, rows)], self.metric, self.normalize, self.precision, self.center)
             # small label copies go FIRST: host->device transfers of every stream share one copy engine queue, so a
             # label copy issued after the feature copies would hold the compute stream until they have all landed
             qp = _as_device(q_pids, torch.int64, self.device)

@@ -55,6 +55,7 @@ class GalleryLabels:
         self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
         self._scratch = torch.empty(64, dtype=torch.int32, device=device)
         self.ready = None
+        self.side_join = False     # the grouping was left on the library's side stream (ieee_gallery_prepare, deferred join)
         if not build:
             return
         with torch.cuda.device(device):
@@ -69,6 +70,14 @@ class GalleryLabels:
                 _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), cur.cuda_stream)
                 self.ready = cur.record_event()
 
+    def wait(self, stream: torch.cuda.Stream, join: bool = True):
+        """Order `stream` after the grouping.  join=False is for the one-call C entry points, which join the library's
+        side stream themselves right before their gather stage."""
+        if self.ready is not None:
+            stream.wait_event(self.ready)
+        if join and self.side_join:
+            _lib.call("ieee_gallery_group_join", stream.cuda_stream)
+
     def list_cap_async(self, q_pids: torch.Tensor, q_ready: torch.cuda.Event):
         """Start the capacity query on the side stream, ordered only after the grouping (`self.ready`) and the query
         ids (`q_ready`) -- NOT after whatever else the compute stream holds, so the caller can queue the contraction
@@ -79,7 +88,7 @@ class GalleryLabels:
         if key not in _PINNED_CAP:
             _PINNED_CAP[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
         host = _PINNED_CAP[key]
-        side.wait_event(self.ready)
+        self.wait(side)
         side.wait_event(q_ready)
         with torch.cuda.stream(side):
             _lib.call("ieee_rank_list_cap", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
@@ -91,6 +100,7 @@ class GalleryLabels:
     def list_cap(self, q_pids: torch.Tensor) -> int:
         cap = C.c_int32(0)
         with torch.cuda.device(q_pids.device):
+            self.wait(torch.cuda.current_stream())
             _lib.call("ieee_rank_list_cap_sync", self.group.data_ptr(), self.G, q_pids.data_ptr(), q_pids.numel(),
                       self._scratch.data_ptr(), C.byref(cap), _lib.stream())
         return max(int(cap.value), 1)

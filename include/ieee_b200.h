@@ -243,15 +243,25 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
                          int32_t cap, float* cmc, ieee_eval_summary* summary, void* workspace, size_t workspace_bytes,
                          ieee_stream_t stream);
 
-/* Gallery side of an evaluation in ONE call: identity grouping (on an internal side stream, joined before return),
- * [centre from the rows of center_src -- normally the query features --] and feature packing.
- * center_src != NULL: its column mean is written to center (float32[D]) and used;  center_src == NULL: center is an
- * INPUT (or NULL: uncentred).  g_pids / group may be NULL to skip the grouping.  workspace:
- * ieee_gallery_prepare_workspace_bytes(D) (only needed with center_src). */
+/* Gallery side of an evaluation in ONE call: identity grouping (on an internal high-priority side stream), [centre
+ * from the query rows q], feature packing of the gallery and, when q_packed is given, of the query rows too.
+ *   q != NULL and no IEEE_PREPARE_KEEP_CENTER: the column mean of (a sample of) q is written to center (float32[D]) and used;
+ *   otherwise center is an INPUT (or NULL: uncentred).
+ *   q_packed != NULL: the Q rows of q are packed there as well (ieee_packed_bytes(Q, D, precision)) and can be handed to
+ *   ieee_retrieve_eval_prepared* -- the caller's host work between the two calls then hides behind that kernel.
+ *   IEEE_PREPARE_DEFER_JOIN: the grouping is left running on the side stream; a stream must call
+ *   ieee_gallery_group_join before it reads `group` (ieee_retrieve_eval_prepared* do that themselves, right before
+ *   their gather stage: the label-only kernels then run beside the contraction instead of holding it up).
+ * g_pids / group may be NULL to skip the grouping.  workspace: ieee_gallery_prepare_workspace_bytes(D) (only needed
+ * when a centre is computed). */
+#define IEEE_PREPARE_DEFER_JOIN 1
+#define IEEE_PREPARE_KEEP_CENTER 2
 size_t ieee_gallery_prepare_workspace_bytes(int64_t D);
 int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int64_t D, int metric, int normalize,
-                         int precision, const int64_t* g_pids, const void* center_src, int64_t ld_src, int64_t rows_src,
-                         float* center, void* g_packed, void* group, void* workspace, ieee_stream_t stream);
+                         int precision, const int64_t* g_pids, const void* q, int64_t ldq, int64_t Q, float* center,
+                         void* g_packed, void* group, void* q_packed, int flags, void* workspace, ieee_stream_t stream);
+/* `stream` waits for the grouping most recently left on this device's side stream (no-op if there is none). */
+int ieee_gallery_group_join(ieee_stream_t stream);
 
 /* The same for a FLOAT64 distance matrix, ranked in float64 order: evaluate_py (rank.py:117, the function this fork
  * runs) argsorts the matrix in the dtype it is given, so distances that differ below float32 resolution are ordered
@@ -293,8 +303,10 @@ int ieee_retrieve_eval_prepared(const void* qf, int64_t ldq, int dtype, int64_t 
                                 const int64_t* q_pids, const int64_t* q_camids, const int64_t* g_camids,
                                 int32_t max_rank, int32_t cap, int32_t* cap_host_out, float* distmat, int64_t ld,
                                 float* cmc, ieee_eval_summary* summary, double* per_query_ap,
-                                int32_t* per_query_first, void* workspace, size_t workspace_bytes,
-                                ieee_stream_t stream);
+                                int32_t* per_query_first,
+                                const void* q_packed /* NULL, or the query rows as packed by ieee_gallery_prepare (qf is
+                                                        then not read and may be NULL) */,
+                                void* workspace, size_t workspace_bytes, ieee_stream_t stream);
 
 /* The same evaluation with the COUNT FUSED INTO THE CONTRACTION's epilogue (F16X3 arithmetic, one query block, one
  * GPU): the Q x G distance block is never written.  A pre-pass computes, in plain fp32, the distance of every query to
@@ -414,7 +426,8 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
                                      int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
                                      const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
                                      ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
-                                     void* workspace, size_t workspace_bytes, ieee_stream_t stream);
+                                     const void* q_packed /* as in ieee_retrieve_eval_prepared */, void* workspace,
+                                     size_t workspace_bytes, ieee_stream_t stream);
 /* Byte offset of a per-query result array inside an exchange buffer: which = 0 AP (double[Qtot]), 1 first hit
  * (int32[Qtot]), 2 mINP term (double[Qtot]), 3 short-list flag (int32[Qtot]). */
 size_t ieee_peer_result_offset(int which, int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards);
