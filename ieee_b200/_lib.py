@@ -37,6 +37,7 @@ SIGNATURES = {
     "ieee_debug_timeline": (C.c_int, [C.c_char_p, sz]),
     "ieee_set_debug_flags": (C.c_int, [C.c_int]),
     "ieee_set_raster_panel": (C.c_int, [C.c_int]),
+    "ieee_set_count_team": (C.c_int, [C.c_int]),
     "ieee_set_centering": (C.c_int, [C.c_int]),
     "ieee_feature_center_workspace_bytes": (sz, [i64]),
     "ieee_feature_center": (C.c_int, [vp, C.c_int, i64, i64, i64, C.c_int, i64, vp, vp, vp]),
@@ -105,7 +106,7 @@ SIGNATURES.update({
     "ieee_peer_result_offset": (sz, [C.c_int, i64, i64, i32, i32, i32]),
     "ieee_retrieve_prepared_peer_workspace_bytes": (sz, [i64, i64, C.c_int, i32]),
     "ieee_retrieve_eval_prepared_peer": (C.c_int, [vp, i64, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, i64, i64, i64,
-                                                   vp, vp, vp, i32, vp, i64, vp, vp, vp, _PEER, vp, vp, sz, vp]),
+                                                   vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, _PEER, vp, vp, sz, vp]),
 })
 
 _lib = None

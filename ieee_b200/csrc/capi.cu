@@ -80,11 +80,13 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
                 const int64_t* g_camids, const void* group, int64_t g_offset, int32_t cap, uint64_t* rel, int32_t* n_rel,
                 uint64_t* junk, int32_t* n_junk, int32_t* overflow, cudaStream_t stream, const PeerView* peers = nullptr);
 size_t rank_count_smem(int shards, int cap);
+int set_count_team(int wpq);
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
                const uint64_t* rel_all, const int32_t* n_rel, const uint64_t* junk, const int32_t* n_junk,
                int32_t* counts, unsigned long long* ties, cudaStream_t stream, const PeerView* peers = nullptr);
 int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
-                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream);
+                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream,
+                      double* ap_out = nullptr, int32_t* first_out = nullptr);
 int rank_count_f64(const double* distmat, int64_t ld, int64_t Q, int64_t G, const int64_t* q_pids, const int64_t* q_camids,
                    const int64_t* g_camids, const void* group, int32_t cap, int32_t* counts, unsigned long long* ties,
                    int32_t* overflow, cudaStream_t stream);
@@ -251,6 +253,8 @@ int ieee_set_centering(int on) {
   if (on >= 0) g_centering = on ? 1 : 0;
   return prev;
 }
+
+int ieee_set_count_team(int warps_per_query) { return set_count_team(warps_per_query); }
 
 int ieee_set_cta_group(int cg) {
   const int prev = cta_group_default();
@@ -874,9 +878,9 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
                                      int precision, const void* g_packed, const void* group, const float* center, int64_t G,
                                      int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
                                      const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
-                                     ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
-                                     const void* q_packed_ready, void* workspace, size_t workspace_bytes,
-                                     ieee_stream_t stream_) {
+                                     ieee_eval_summary* summary, int64_t* stats_out, double* per_query_ap,
+                                     int32_t* per_query_first, const ieee_peer_exchange* ex, const void* q_packed_ready,
+                                     void* workspace, size_t workspace_bytes, ieee_stream_t stream_) {
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -915,7 +919,10 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
                                   stream_)))
     return rc;
   if ((rc = ieee_rank_count_peer(distmat, ld, G, g_offset, n_rel, junk, n_junk, stats, ex, stream_))) return rc;
-  return ieee_rank_metrics_peer(G_total, max_rank, stats, cmc, summary, stats_out, ex, stream_);
+  PeerView v;
+  if ((rc = peer_view(ex, &v))) return rc;
+  return rank_metrics_peer(&v, G_total, max_rank, stats, cmc, summary, reinterpret_cast<long long*>(stats_out), ex->Qtot, stream,
+                           per_query_ap, per_query_first);
 }
 
 size_t ieee_peer_result_offset(int which, int64_t Qb_max, int64_t Qtot, int32_t cap, int32_t W, int32_t shards) {

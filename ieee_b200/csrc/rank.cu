@@ -149,6 +149,9 @@ int rank_list_cap(const void* group, int64_t G, const int64_t* q_pids, int64_t Q
 // ---------------------------------------------------------------------------------------------------------
 // gather: one warp per query.  rank.py:136: junk = same pid AND same camera; relevant = same pid, other camera.
 // ---------------------------------------------------------------------------------------------------------
+// With a peer exchange the CTA's eight list rows are staged in shared memory and then copied, as ONE contiguous chunk
+// of 8 * (cap + 1) words, into slot `my` of every rank's list table: per-lane 8-byte stores over NVLink (one 40 - 70 byte
+// transaction per query and peer) made the kernel 45 us at N = 8.  `stage` = 0 when the rows do not fit (cap > 255).
 __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
                                                            const int64_t* __restrict__ q_pids, const int64_t* __restrict__ q_camids,
                                                            const int64_t* __restrict__ g_camids, const long long* __restrict__ keys,
@@ -156,48 +159,64 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const float* __restric
                                                            const int32_t* __restrict__ members, int64_t T, int64_t g_offset,
                                                            int32_t cap, uint64_t* __restrict__ rel, int32_t* __restrict__ n_rel,
                                                            uint64_t* __restrict__ junk, int32_t* __restrict__ n_junk,
-                                                           int32_t* __restrict__ overflow, const PeerView pv) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= Q) return;
-  // peer exchange: this shard's list goes straight into slot `my` of EVERY rank's list table (posted NVLink stores;
-  // the count kernel hands over with the phase-A flags), instead of a local list + all-gather
+                                                           int32_t* __restrict__ overflow, const PeerView pv, int stage) {
+  extern __shared__ __align__(16) uint64_t g_stage[];          // [8][cap + 1] when staging
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t q0 = (int64_t)blockIdx.x * (blockDim.x >> 5);
+  const int64_t q = q0 + w;
+  const bool staged = pv.shards != 0 && stage != 0;
+  // peer exchange: this shard's list goes into slot `my` of EVERY rank's list table (posted NVLink stores; the count
+  // kernel hands over with the phase-A flags), instead of a local list + all-gather
   auto put_rel = [&](int slot, uint64_t v) {
     if (pv.shards == 0) { rel[q * (cap + 1) + slot] = v; return; }
+    if (staged) { g_stage[w * (cap + 1) + slot] = v; return; }
     for (int p = 0; p < pv.shards; ++p)
       (reinterpret_cast<uint64_t*>(pv.base[p] + pv.off_rel) + ((int64_t)pv.my * Q + q) * (cap + 1))[slot] = v;
   };
-  const int64_t cam = q_camids[q];
-  int lo = 0, n = 0;
-  if (lane == 0) {
-    const int s = group_find(keys, T, q_pids[q]);
-    if (s >= 0) { lo = goff[s]; n = gcnt[s]; }
-  }
-  lo = __shfl_sync(0xffffffffu, lo, 0);
-  n = __shfl_sync(0xffffffffu, n, 0);
-  int nr = 0, nj = 0;
-  for (int t0 = 0; t0 < n; t0 += 32) {
-    const int t = t0 + lane;
-    bool is_rel = false, is_junk = false;
-    uint64_t key = 0;
-    if (t < n) {
-      const int32_t gi = members[lo + t];
-      key = pack_key(distmat[q * ld + gi], (uint32_t)(gi + g_offset));
-      is_junk = g_camids[gi] == cam;
-      is_rel = !is_junk;
+  if (q < Q) {
+    const int64_t cam = q_camids[q];
+    int lo = 0, n = 0;
+    if (lane == 0) {
+      const int s = group_find(keys, T, q_pids[q]);
+      if (s >= 0) { lo = goff[s]; n = gcnt[s]; }
     }
-    const unsigned mr = __ballot_sync(0xffffffffu, is_rel), mj = __ballot_sync(0xffffffffu, is_junk);
-    const unsigned below = (1u << lane) - 1;
-    if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) put_rel(s, key); }
-    if (is_junk) { const int s = nj + __popc(mj & below); if (s < cap) junk[q * cap + s] = key; }
-    nr += __popc(mr);
-    nj += __popc(mj);
+    lo = __shfl_sync(0xffffffffu, lo, 0);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    int nr = 0, nj = 0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+      const int t = t0 + lane;
+      bool is_rel = false, is_junk = false;
+      uint64_t key = 0;
+      if (t < n) {
+        const int32_t gi = members[lo + t];
+        key = pack_key(distmat[q * ld + gi], (uint32_t)(gi + g_offset));
+        is_junk = g_camids[gi] == cam;
+        is_rel = !is_junk;
+      }
+      const unsigned mr = __ballot_sync(0xffffffffu, is_rel), mj = __ballot_sync(0xffffffffu, is_junk);
+      const unsigned below = (1u << lane) - 1;
+      if (is_rel) { const int s = nr + __popc(mr & below); if (s < cap) put_rel(s, key); }
+      if (is_junk) { const int s = nj + __popc(mj & below); if (s < cap) junk[q * cap + s] = key; }
+      nr += __popc(mr);
+      nj += __popc(mj);
+    }
+    if (lane == 0) {
+      if (nr > cap || nj > cap) { atomicMax(overflow, max(nr, nj)); nr = min(nr, cap); nj = min(nj, cap); }
+      n_rel[q] = nr;
+      put_rel(cap, (uint64_t)nr);                   // the list carries its own length: one exchange moves both
+      n_junk[q] = nj;
+    }
   }
-  if (lane == 0) {
-    if (nr > cap || nj > cap) { atomicMax(overflow, max(nr, nj)); nr = min(nr, cap); nj = min(nj, cap); }
-    n_rel[q] = nr;
-    put_rel(cap, (uint64_t)nr);                   // the list carries its own length: one exchange moves both
-    n_junk[q] = nj;
+  if (!staged) return;
+  __syncthreads();
+  // rows q0 .. q0 + 7 are adjacent in every table: one chunk per peer, 8-byte words, consecutive threads -> consecutive
+  // words (entries past a list's length are whatever the staging area held: nobody reads them)
+  const int64_t left = Q - q0;
+  const int rows = left < (int64_t)(blockDim.x >> 5) ? (int)left : (int)(blockDim.x >> 5);
+  const int words = rows * (cap + 1);
+  for (int p = 0; p < pv.shards; ++p) {
+    uint64_t* dst = reinterpret_cast<uint64_t*>(pv.base[p] + pv.off_rel) + ((int64_t)pv.my * Q + q0) * (cap + 1);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = g_stage[i];
   }
 }
 
@@ -506,6 +525,7 @@ __device__ __forceinline__ CountRow count_row(int32_t* counts, int64_t q, int st
 // take the generic search with shared atomics.  Longer lists go to rank_count_kernel below.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWarpQ = 8;            // warps per CTA
+constexpr int kCountTeamDefault = 1;  // warps per query for rows of 4 K .. 64 K columns
 constexpr int kWarpRmax = 128;       // thresholds per query the private table holds (cell words address up to 511 bins)
 struct WarpMisc { float lo, scale, top; int R, use_lut, ties; uint32_t kmax; int pad; };   // 32 bytes
 // T[rmax] u64 | hist[rmax + 2] | cell[1024 + 4] u16 | misc (32 B) | priv[wpq][rmax + 2][32]   (priv 8-byte aligned: it
@@ -520,20 +540,26 @@ rank_count_warp_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q,
                        int out_cap, int rmax, const uint64_t* __restrict__ rel_all, const int32_t* __restrict__ n_rel,
                        const uint64_t* __restrict__ junk, const int32_t* __restrict__ n_junk, int32_t* __restrict__ counts,
                        unsigned long long* __restrict__ ties_out, const PeerView pv) {
-  static_assert(WPQ == 1 || WPQ == kWarpQ, "one warp or the whole CTA per query");
+  static_assert(WPQ == 1 || WPQ == 2 || WPQ == 4 || WPQ == kWarpQ, "1, 2, 4 or all 8 warps of the CTA per query");
   if (pv.shards) peer_signal_and_wait(pv, 0);      // every shard's relevant lists have landed in rel_all
   constexpr bool kTeam = WPQ > 1;
+  constexpr int kTeams = kWarpQ / WPQ;             // queries per CTA
   extern __shared__ __align__(16) uint8_t ws_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int wq = kTeam ? w : 0;                                                       // this warp's place in its team
-  uint8_t* mine = ws_raw + (kTeam ? size_t(0) : size_t(w) * warp_smem_per_query(rmax, 1));
+  const int team = w / WPQ, wq = w % WPQ;                                             // this warp's team and place in it
+  uint8_t* mine = ws_raw + size_t(team) * warp_smem_per_query(rmax, WPQ);
   uint64_t* T = reinterpret_cast<uint64_t*>(mine);                                   // [rmax]
   int32_t* hist = reinterpret_cast<int32_t*>(mine + rmax * 8);                        // [rmax + 2]
   uint16_t* cell = reinterpret_cast<uint16_t*>(hist + rmax + 2);                      // [1024 + 4]
   WarpMisc* misc = reinterpret_cast<WarpMisc*>(cell + kLutCells + 4);
   int32_t* priv = reinterpret_cast<int32_t*>(misc + 1) + size_t(wq) * (rmax + 2) * 32;   // this warp's [rmax + 2][32]
-  auto team_sync = [&]() { if constexpr (kTeam) __syncthreads(); else __syncwarp(); };
-  const int64_t q = kTeam ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * kWarpQ + w;
+  // a team's warps meet at their own named barrier (ids 1 .. kTeams; 0 is __syncthreads'): teams run independently
+  auto team_sync = [&]() {
+    if constexpr (WPQ == kWarpQ) __syncthreads();
+    else if constexpr (kTeam) asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(32 * WPQ) : "memory");
+    else __syncwarp();
+  };
+  const int64_t q = (int64_t)blockIdx.x * kTeams + team;
   if (q >= Q) return;
   const int stride = out_cap + 2;
   const CountRow out = count_row(counts, q, stride, pv);
@@ -906,6 +932,22 @@ static int count_warp_max_g() {
   return v;
 }
 
+// team size for rows of 4 K .. 64 K columns (ieee_set_count_team / IEEE_B200_COUNT_WPQ = 1 | 2 | 4 | 8)
+static int g_count_team = -1;
+static int count_team_mid() {
+  if (g_count_team < 0) {
+    const char* e = getenv("IEEE_B200_COUNT_WPQ");
+    const int v = e ? atoi(e) : kCountTeamDefault;
+    g_count_team = (v == 1 || v == 2 || v == 4 || v == 8) ? v : kCountTeamDefault;
+  }
+  return g_count_team;
+}
+int set_count_team(int wpq) {
+  const int prev = count_team_mid();
+  if (wpq == 1 || wpq == 2 || wpq == 4 || wpq == 8) g_count_team = wpq;
+  return prev;
+}
+
 size_t rank_count_smem(int shards, int cap) { return count_smem_plan(next_pow2(max(shards * cap, 2))).total; }
 
 int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g_offset, int shards, int cap, int out_cap,
@@ -919,14 +961,24 @@ int rank_count(const float* distmat, int64_t ld, int64_t Q, int64_t G, int64_t g
   if (out_cap == 0 || out_cap > shards * cap) out_cap = shards * cap;       // a merged list cannot be longer than this
   if (out_cap <= kWarpRmax && !(g_debug_flags & 16)) {
     const int rmax = (out_cap + 1) & ~1;           // even: keeps the 8-byte alignment of every query's T
-    const bool team = G > count_warp_max_g();      // long rows: the whole CTA streams one query
-    const size_t wsmem = team ? size_t(warp_smem_per_query(rmax, kWarpQ)) : size_t(kWarpQ) * warp_smem_per_query(rmax, 1);
-    auto kern = team ? rank_count_warp_kernel<kWarpQ> : rank_count_warp_kernel<1>;
-    if (team) IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<kWarpQ>, wsmem);
-    else IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<1>, wsmem);
-    const unsigned grid = team ? (unsigned)Q : (unsigned)((Q + kWarpQ - 1) / kWarpQ);
-    kern<<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, rel_all, n_rel,
-                                               junk, n_junk, counts, ties, pv);
+    // warps per query: long rows (a C4 shard) take the whole CTA; Market-sized rows a team of `count_team_mid()` warps
+    // -- 3368 one-warp rows are 0.7 of ONE wave on 148 SMs, so every warp's set-up phase coincided and nothing
+    // streamed meanwhile; teams make more, shorter rows of work, and set-up overlaps streaming across waves
+    const int wpq = G > count_warp_max_g() ? kWarpQ : (G >= 4096 ? count_team_mid() : 1);
+    const int teams = kWarpQ / wpq;
+    const size_t wsmem = size_t(teams) * warp_smem_per_query(rmax, wpq);
+    const unsigned grid = (unsigned)((Q + teams - 1) / teams);
+#define IEEE_COUNT_LAUNCH(W)                                                                                                   \
+  do {                                                                                                                         \
+    IEEE_ENSURE_DYN_SMEM(rank_count_warp_kernel<W>, wsmem);                                                                    \
+    rank_count_warp_kernel<W><<<grid, 32 * kWarpQ, wsmem, stream>>>(distmat, ld, Q, (int)G, g_offset, shards, cap, out_cap, rmax, \
+                                                                    rel_all, n_rel, junk, n_junk, counts, ties, pv);           \
+  } while (0)
+    if (wpq == kWarpQ) IEEE_COUNT_LAUNCH(kWarpQ);
+    else if (wpq == 4) IEEE_COUNT_LAUNCH(4);
+    else if (wpq == 2) IEEE_COUNT_LAUNCH(2);
+    else IEEE_COUNT_LAUNCH(1);
+#undef IEEE_COUNT_LAUNCH
     count_launch(1, "rank_count_warp_kernel");
     IEEE_CUDA_CHECK(cudaGetLastError());
     return IEEE_OK;
@@ -952,9 +1004,11 @@ int rank_gather(const float* distmat, int64_t ld, int64_t Q, int64_t G, const in
   IEEE_REQUIRE(g_offset >= 0 && g_offset + G <= (int64_t(1) << 32), "rank_gather: global gallery index must fit 32 bits");
   if (Q == 0) return IEEE_OK;
   GroupView v = group_view(group, G);
-  rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.keys, v.cnt,
-                                                                  v.off, v.members, v.T, g_offset, cap, rel, n_rel, junk, n_junk,
-                                                                  overflow, pv);
+  const int stage = (pv.shards != 0 && cap <= 255) ? 1 : 0;
+  const size_t smem = stage ? size_t(8) * (cap + 1) * 8 : 0;
+  rank_gather_kernel<<<(unsigned)((Q + 7) / 8), 256, smem, stream>>>(distmat, ld, Q, G, q_pids, q_camids, g_camids, v.keys, v.cnt,
+                                                                     v.off, v.members, v.T, g_offset, cap, rel, n_rel, junk, n_junk,
+                                                                     overflow, pv, stage);
   count_launch(1, "rank_gather_kernel");
   IEEE_CUDA_CHECK(cudaGetLastError());
   return IEEE_OK;
@@ -1158,9 +1212,11 @@ __global__ void __launch_bounds__(1024) rank_metrics_kernel(const int32_t* __res
 }
 
 // Peer exchange, last stage of a query block (see rank_metrics_kernel).  cmc / summary / stats_out are written when
-// the block is the last one of the evaluation (q_base + Qb == Qtot).
+// the block is the last one of the evaluation (q_base + Qb == Qtot).  ap_out / first_out (arrays of Qtot entries, may
+// be null) replace the per-query AP / first-hit arrays of the exchange buffer: the results are local to each rank.
 int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, const unsigned long long* local_stats,
-                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream) {
+                      float* cmc, ieee_eval_summary* summary, long long* stats_out, int64_t Qtot, cudaStream_t stream,
+                      double* ap_out, int32_t* first_out) {
   IEEE_REQUIRE(peers && peers->shards >= 1 && local_stats, "rank_metrics_peer: needs a peer exchange");
   IEEE_REQUIRE(max_rank >= 1 && max_rank <= 8192, "rank_metrics_peer: bad shape (max_rank=%d)", max_rank);
   if (max_rank > G_total) max_rank = (int32_t)G_total;
@@ -1171,8 +1227,8 @@ int rank_metrics_peer(const PeerView* peers, int64_t G_total, int32_t max_rank, 
   const size_t smem = 2 * 1024 * 8 + size_t(max_rank + 1) * 4;
   IEEE_ENSURE_DYN_SMEM(rank_metrics_kernel, smem);
   rank_metrics_kernel<<<(unsigned)((v.Qb + 31) / 32), 1024, smem, stream>>>(
-      nullptr, v.Qb, G_total, v.W + 2, max_rank, reinterpret_cast<double*>(mine + v.off_ap),
-      reinterpret_cast<int32_t*>(mine + v.off_first), reinterpret_cast<int32_t*>(mine + v.off_short),
+      nullptr, v.Qb, G_total, v.W + 2, max_rank, ap_out ? ap_out : reinterpret_cast<double*>(mine + v.off_ap),
+      first_out ? first_out : reinterpret_cast<int32_t*>(mine + v.off_first), reinterpret_cast<int32_t*>(mine + v.off_short),
       reinterpret_cast<double*>(mine + v.off_inp), nullptr, cmc, summary, nullptr,
       reinterpret_cast<uint32_t*>(mine + kPeerTicketOffset), v, local_stats, stats_out, last, Qtot);
   count_launch(1, "rank_metrics_kernel (peer)");

@@ -603,6 +603,10 @@ class RetrievalEvaluator:
                 buf = _FUSED_POOL[key] = (ws, res, torch.empty(res.shape, dtype=torch.uint8, pin_memory=True))
             ws, res, res_host = buf
             self._ensure_block(Q)
+            # per-query results straight into fresh arrays (every rank derives all of them itself): nothing to copy out
+            # of the exchange buffer after the result has arrived, when the GPU would be idle
+            ap = torch.empty(Q, dtype=torch.float64, device=self.device)
+            first = torch.empty(Q, dtype=torch.int32, device=self.device)
             cur = torch.cuda.current_stream()
             self.labels.wait(cur, join=False)
             gpk = self.chunks[0][1]
@@ -611,7 +615,7 @@ class RetrievalEvaluator:
                       _lib.METRICS[self.metric], int(self.normalize), prec, gpk.buf.data_ptr(), self.labels.group.data_ptr(),
                       _lib.ptr(self.center), self.G, self.g_total, self.g_offset, qp.data_ptr(), qc.data_ptr(),
                       self.labels.camids.data_ptr(), self.max_rank, self._block.data_ptr(), self._block.stride(0),
-                      res.data_ptr() + 96, res.data_ptr() + 32, res.data_ptr(), C.byref(ex),
+                      res.data_ptr() + 96, res.data_ptr() + 32, res.data_ptr(), ap.data_ptr(), first.data_ptr(), C.byref(ex),
                       qpk.buf.data_ptr() if qpk is not None else None, ws.data_ptr(), ws.numel(), cur.cuda_stream)
             res_host.copy_(res, non_blocking=True)
             cur.synchronize()
@@ -622,10 +626,6 @@ class RetrievalEvaluator:
                 return self.evaluate(qf, q_pids, q_camids, return_distmat, use_cap_memo=False, one_call=False)
             summary = _lib.EvalSummary.from_buffer_copy(out[32:96].tobytes())
             cmc_host = out[96:].view(np.float32).copy()
-            offs = [lib.ieee_peer_result_offset(i, Q, Q, cap, W, self.world) for i in (0, 1)]
-            # every rank holds all per-query results; copied out because the next evaluation overwrites the buffer
-            ap = link.view[offs[0]: offs[0] + 8 * Q].view(torch.float64).clone()
-            first = link.view[offs[1]: offs[1] + 4 * Q].view(torch.int32).clone()
         raise_for_status(summary, self.max_rank)
         info = {"num_valid": summary.num_valid, "num_ties": summary.num_ties, "cap": cap, "ap": ap, "first": first,
                 "mINP": float(summary.mINP)}

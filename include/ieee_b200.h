@@ -78,6 +78,10 @@ int ieee_set_accum_chunk(int k_slices);
  * fastest, so one panel's query rows stay L2-resident while it sweeps every gallery tile.  0 (default) sizes the
  * panel for ~40 MB of query operand.  Negative: query only.  Returns the previous value. */
 int ieee_set_raster_panel(int m_tiles);
+/* Warps that stream one query's distance row together in the count stage, for rows of 4 K .. 64 K columns: 1, 2, 4 or
+ * 8 (shorter rows always take one warp, longer ones the whole CTA of 8).  Other values: query only.  Returns the
+ * previous value.  Results do not depend on it. */
+int ieee_set_count_team(int warps_per_query);
 /* Whether the one-call entry points (ieee_distmat, ieee_retrieve_eval) centre euclidean operands on the query
  * set's mean (see ieee_feature_center).  Default 1; 0 reproduces the uncentred arithmetic of ABI 2 (accuracy
  * studies).  Negative: query only.  Returns the previous value. */
@@ -425,7 +429,9 @@ int ieee_retrieve_eval_prepared_peer(const void* qf, int64_t ldq, int dtype, int
                                      int precision, const void* g_packed, const void* group, const float* center, int64_t G,
                                      int64_t G_total, int64_t g_offset, const int64_t* q_pids, const int64_t* q_camids,
                                      const int64_t* g_camids, int32_t max_rank, float* distmat, int64_t ld, float* cmc,
-                                     ieee_eval_summary* summary, int64_t* stats_out, const ieee_peer_exchange* ex,
+                                     ieee_eval_summary* summary, int64_t* stats_out,
+                                     double* per_query_ap /* double[Q], may be NULL: then in the exchange buffer */,
+                                     int32_t* per_query_first /* int32[Q], may be NULL */, const ieee_peer_exchange* ex,
                                      const void* q_packed /* as in ieee_retrieve_eval_prepared */, void* workspace,
                                      size_t workspace_bytes, ieee_stream_t stream);
 /* Byte offset of a per-query result array inside an exchange buffer: which = 0 AP (double[Qtot]), 1 first hit

@@ -91,6 +91,38 @@ def test_heavy_ties_and_special_values():
     check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
 
 
+_team_ties = []
+
+
+@pytest.mark.parametrize("team", [1, 2, 4, 8])
+def test_count_team_sizes_give_identical_results(team):
+    """Rows of 4 K .. 64 K columns are streamed by 1, 2, 4 or 8 warps per query (ieee_set_count_team): ragged row
+    length, heavy ties, NaN / inf, invalid queries, a query count that does not fill the last CTA."""
+    lib = _lib.load()
+    rng = np.random.RandomState(77)
+    Q, G = 157, 9001
+    d = np.round(rng.rand(Q, G) * 300).astype(np.float32)          # ~30 equal values per level
+    d[3, ::11] = np.nan
+    d[4, :40] = np.inf
+    d[5, 100:140] = -np.inf
+    d[6, :] = 2.0
+    qp, gp = rng.randint(0, 60, Q), rng.randint(0, 64, G)          # identities 60 .. 63 are never queried
+    qp[7] = 10 ** 12                                               # not in the gallery: invalid query
+    qc, gc = rng.randint(0, 3, Q), rng.randint(0, 3, G)
+    prev = lib.ieee_set_count_team(team)
+    try:
+        assert lib.ieee_set_count_team(-1) == team
+        check_against_oracle(d, qp, gp, qc, gc, max_rank=20)
+        dd = torch.from_numpy(d).cuda()
+        _, summary, st = evaluate_device(dd, qp, gp, qc, gc, 20)
+        _, _, info = R.eval_market1501(d, qp, gp, qc, gc, 20, return_info=True)
+        assert np.array_equal(st.first.cpu().numpy(), info["first_hit"])
+        _team_ties.append(int(summary.num_ties))
+        assert len(set(_team_ties)) == 1 and _team_ties[0] > 0              # the tie statistic does not depend on the team size either
+    finally:
+        lib.ieee_set_count_team(prev)
+
+
 @pytest.mark.parametrize("G", [700, 70000])        # warp-per-query kernel / CTA-per-query kernel
 def test_degenerate_threshold_spans(G):
     """One relevant item per query, two at the same distance, two one ulp apart, a huge span: the cell table must
