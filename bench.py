@@ -24,6 +24,7 @@ Besides the timed headline the line carries, on rank 0:
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -60,6 +61,7 @@ def bench_config(n_gpus: int) -> dict:
     n = max(1, n_gpus)
     return {"workload": f"market1501_shaped Q={Q_BASE * n} G={G_TOTAL} D={DIM} euclidean max_rank={MAX_RANK}",
             "gallery_sharding": f"{n} contiguous row shards", "queries": "replicated on every rank",
+            "timing": "cyclic GC off inside the timed loops of both arms (as timeit does)",
             "l2": "per-step working set (features 178 MB + packed 178 MB + distmat 214 MB per GPU) exceeds the 126 MB L2; "
                   "stage timings flush L2 with a 256 MB write between repetitions"}
 
@@ -119,7 +121,7 @@ class ClockSampler:
         def run():
             while not self._stop.is_set():
                 self.sample()
-                self._stop.wait(0.003)
+                self._stop.wait(0.005)
 
         self._thread = threading.Thread(target=run, daemon=True)
         self._thread.start()
@@ -132,7 +134,7 @@ class ClockSampler:
             self._thread = None
 
     def result(self):
-        how = {"thread": "NVML readings by a sampling thread (every ~3 ms) while the timed region runs",
+        how = {"thread": "NVML readings by a sampling thread (every ~5 ms) while the timed region runs",
                "loop": "NVML readings taken by the timing loop between steps of the timed region",
                "after": "NVML readings between steps of a second pass of the same K steps that follows the timed region at once "
                         "(no reading inside the timed region itself)"}[self.mode]
@@ -162,12 +164,17 @@ def time_cpu_path(qf, gf, q_pids, g_pids, q_camids, g_camids, metric, steps, war
     torch.set_num_threads(cores)
     kind, ref = cpu_reference_path()
     times = []
+    gc_was_on = gc.isenabled()
+    gc.collect()
+    gc.disable()                 # same rule as our arm's timed loop
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         d = ref.compute_distance_matrix(qf, gf, metric).numpy()
         ref.evaluate_cy(d, q_pids, g_pids, q_camids, g_camids, MAX_RANK)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+    if gc_was_on:
+        gc.enable()
     return sum(times) / len(times), kind, cores
 
 
@@ -480,6 +487,12 @@ def run_ours(args):
         # rank 0's start event the other ranks' clocks were already running while they waited for rank 0's lists
         # (N = 2 read 1.29 ms per step instead of 0.88; N = 4 once 6.6 ms)
         sampler = ClockSampler(local_rank, enabled=rank == 0)      # rank 0 samples; the others stay quiet
+        # as timeit does: no cyclic-GC pause inside the timed loop (a generation-2 collection of a process that has
+        # imported torch takes milliseconds; with N ranks in lock step every rank waits for whoever collects).
+        # Collected and switched off BEFORE the warm-up, for the same reason NVML is opened there.
+        gc_was_on = gc.isenabled()
+        gc.collect()
+        gc.disable()
         for _ in range(warmup):
             fn()
         barrier()
@@ -494,6 +507,8 @@ def run_ours(args):
                 sampler.sample()
         stop.record()
         sampler.stop()
+        if gc_was_on:
+            gc.enable()
         launches = lib.ieee_launch_count() - l0
         if sampler.mode == "after":
             for i in range(steps):
