@@ -1453,28 +1453,93 @@ __device__ int topk_stream_path(const TopkArgs& a, uint64_t* cand, int* count_s,
   return *count_s;
 }
 
-// Fast path (k <= kTopkFastMaxK): every thread keeps the minimum packed key of its strided share of the row; the
-// m-th smallest of those 256 minima is >= the m-th smallest element of the row, so with m = 2k + 8 (head-room for
-// junk entries) it bounds the k-th smallest kept element unless more than k + 8 of the leaders are junk.  A second
-// pass over the (L2-resident) row collects the few elements below that bound.  Returns the candidate count, or -1
-// when the bound left fewer than k kept candidates / overflowed (the caller then takes the general path).
+// ascending bitonic sort of one 64-bit key per lane across a warp (registers + shuffles, no barrier)
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+      v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  return v;
+}
+
+// Fast path (k <= kTopkFastMaxK): every thread keeps the leader of its strided share of the row (smallest distance,
+// lowest index among equals); the m-th smallest of those 256 leaders is >= the m-th smallest element of the row, so
+// with m = 2k + 8 (head-room for junk entries) it bounds the k-th smallest kept element unless more than k + 8 of
+// the leaders are junk.  A second pass over the (L2-resident) row collects the few elements below that bound.
+// Both passes read 16-byte vectors and decide with plain float compares -- a thread walks its share in increasing
+// index order, so `d < best` keeps the earliest of equal distances (-0 == +0 as in the key order), NaN never leads
+// (it ranks last) -- and only leaders / candidates get a packed 64-bit key: the round-1 version built a key per
+// element in both passes (93 M warp instructions for 54 M elements).  Returns the candidate count, or -1 when the
+// bound left fewer than k kept candidates / overflowed (the caller then takes the general path).
 __device__ int topk_select_path(const TopkArgs& a, uint64_t* cand, int* count_s) {
   const int tid = threadIdx.x;
-  uint64_t best = kPadKey;
-  for (int64_t g = tid; g < a.G; g += kTopkThreads) {
-    const uint64_t pe = pack_key(a.row[g], (uint32_t)(g + a.g_offset));
-    best = pe < best ? pe : best;
+  const float* __restrict__ row = a.row;
+  const int G = (int)a.G;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
+  int head = (int)(((16 - (addr & 15)) & 15) >> 2);
+  if (head > G) head = G;
+  const int nvec = (G - head) >> 2;
+  const float4* rv = reinterpret_cast<const float4*>(row + head);
+  float bd = __int_as_float(0x7f800000);
+  int bg = -1;
+  auto lead = [&](float d, int g) { if (d < bd) { bd = d; bg = g; } };
+  for (int g = tid; g < head; g += kTopkThreads) lead(row[g], g);
+  int i = tid;
+  for (; i + 3 * kTopkThreads < nvec; i += 4 * kTopkThreads) {          // four independent 16-byte loads in flight
+    const float4 v0 = __ldg(rv + i), v1 = __ldg(rv + i + kTopkThreads), v2 = __ldg(rv + i + 2 * kTopkThreads),
+                 v3 = __ldg(rv + i + 3 * kTopkThreads);
+    int g = head + 4 * i;
+    lead(v0.x, g); lead(v0.y, g + 1); lead(v0.z, g + 2); lead(v0.w, g + 3);
+    g += 4 * kTopkThreads;
+    lead(v1.x, g); lead(v1.y, g + 1); lead(v1.z, g + 2); lead(v1.w, g + 3);
+    g += 4 * kTopkThreads;
+    lead(v2.x, g); lead(v2.y, g + 1); lead(v2.z, g + 2); lead(v2.w, g + 3);
+    g += 4 * kTopkThreads;
+    lead(v3.x, g); lead(v3.y, g + 1); lead(v3.z, g + 2); lead(v3.w, g + 3);
   }
-  cand[tid] = best;
-  if (tid == 0) *count_s = 0;
-  block_bitonic_sort(cand, kTopkThreads);
-  const int m = min(2 * a.k + 8, kTopkThreads) - 1;
-  const uint64_t tau = cand[m];
+  for (; i < nvec; i += kTopkThreads) {
+    const float4 v = __ldg(rv + i);
+    const int g = head + 4 * i;
+    lead(v.x, g); lead(v.y, g + 1); lead(v.z, g + 2); lead(v.w, g + 3);
+  }
+  for (int g = head + 4 * nvec + tid; g < G; g += kTopkThreads) lead(row[g], g);
+  // (a share that holds nothing below +inf has no leader: a pad key, which can only raise the bound)
+  // the m-th smallest leader, without sorting all 256 in shared memory (36 barrier-separated stages were a third of
+  // the kernel's instructions): every warp sorts its 32 leaders in registers, the eight sorted runs go to shared
+  // memory, and each thread ranks its own leader by binary search in the seven other runs.  Real leaders are distinct
+  // (distinct gallery indices), so exactly one thread finds rank m -- unless fewer than m + 1 shares have a leader.
+  const int lane = tid & 31, w = tid >> 5;
+  const uint64_t mine = warp_sort_u64(bg >= 0 ? pack_key(bd, (uint32_t)(bg + a.g_offset)) : kPadKey, lane);
+  __shared__ uint64_t tau_sel;
+  cand[tid] = mine;
+  if (tid == 0) { *count_s = 0; tau_sel = kPadKey; }
   __syncthreads();
-  if (tau == kPadKey) return -1;             // fewer than m+1 populated threads (tiny rows): general path
+  const int m = min(2 * a.k + 8, kTopkThreads) - 1;
+  if (mine != kPadKey) {
+    int rank = lane;
+    for (int r = 0; r < kTopkThreads / 32; ++r) {
+      if (r == w) continue;
+      const uint64_t* run = cand + r * 32;
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (run[lo + step - 1] < mine) lo += step;
+      lo += run[lo] < mine ? 1 : 0;             // (lo <= 31 here)
+      rank += lo;
+    }
+    if (rank == m) tau_sel = mine;
+  }
+  __syncthreads();
+  const uint64_t tau = tau_sel;
+  __syncthreads();                           // (cand is reused below)
+  if (tau == kPadKey) return -1;             // fewer than m+1 leaders (tiny rows, rows of inf / NaN): general path
   const float tau_d = key_to_float((uint32_t)(tau >> 32));
-  for (int64_t g = tid; g < a.G; g += kTopkThreads) {
-    const float d = a.row[g];
+  auto collect = [&](float d, int g) {
     if (!(d > tau_d)) {                      // cheap float pre-filter (NaN passes and is decided by the key compare)
       const uint64_t pe = pack_key(d, (uint32_t)(g + a.g_offset));
       if (pe <= tau) {
@@ -1485,7 +1550,14 @@ __device__ int topk_select_path(const TopkArgs& a, uint64_t* cand, int* count_s)
         }
       }
     }
+  };
+  for (int g = tid; g < head; g += kTopkThreads) collect(row[g], g);
+  for (i = tid; i < nvec; i += kTopkThreads) {
+    const float4 v = __ldg(rv + i);
+    const int g = head + 4 * i;
+    collect(v.x, g); collect(v.y, g + 1); collect(v.z, g + 2); collect(v.w, g + 3);
   }
+  for (int g = head + 4 * nvec + tid; g < G; g += kTopkThreads) collect(row[g], g);
   __syncthreads();
   const int n = *count_s;
   __syncthreads();
@@ -1521,12 +1593,27 @@ topk_kernel(const float* __restrict__ distmat, int64_t ld, int64_t Q, int64_t G,
     __syncthreads();
     n = topk_stream_path(a, cand, &count, &tau_s);
   }
-  const int np = next_pow2(max(n, 2));
-  for (int i = n + tid; i < np; i += kTopkThreads) cand[i] = kPadKey;
-  block_bitonic_sort(cand, np);
+  const uint64_t* sorted = cand;
+  if (n <= 128) {
+    // few candidates (the usual case: about 2k + 8): every candidate's position is the number of smaller ones
+    // (distinct keys) -- one pass of broadcast loads for the first n threads instead of a barrier-separated sort
+    __syncthreads();
+    if (tid < n) {
+      const uint64_t v = cand[tid];
+      int pos = 0;
+      for (int j = 0; j < n; ++j) pos += cand[j] < v ? 1 : 0;
+      cand[kTopkBuf / 2 + pos] = v;
+    }
+    __syncthreads();
+    sorted = cand + kTopkBuf / 2;
+  } else {
+    const int np = next_pow2(max(n, 2));
+    for (int i = n + tid; i < np; i += kTopkThreads) cand[i] = kPadKey;
+    block_bitonic_sort(cand, np);
+  }
   for (int i = tid; i < k; i += kTopkThreads) {
     if (i < n) {
-      const uint32_t gi = (uint32_t)cand[i];
+      const uint32_t gi = (uint32_t)sorted[i];
       idx_out[q * k + i] = (int32_t)gi;
       val_out[q * k + i] = a.row[(int64_t)gi - g_offset];
     } else {
