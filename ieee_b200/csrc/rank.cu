@@ -473,9 +473,20 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane,
   };
   for (int g = t0; g < head; g += S) one(g);
   int i = t0;
-  for (; i + 3 * S < nvec; i += 4 * S) {     // 4 independent 16-byte loads in flight per lane
-    // plain (L1-allocating) loads: the rare exact pass below re-reads a distance, and finds it in L1
-    const float4 a0 = __ldg(rv + i), a1 = __ldg(rv + i + S), a2 = __ldg(rv + i + 2 * S), a3 = __ldg(rv + i + 3 * S);
+  // 4 independent 16-byte loads per lane and batch, software-pipelined: the NEXT batch's loads are issued before the
+  // current batch is processed (the compiler places them right after the last use of the current values, a third of
+  // the way into the body), so a warp's ~200 instructions of binning overlap its own load latency -- with ~23 warps
+  // per SM (3368 rows are 0.7 of a wave) there are not enough other warps to hide it.  ncu at the Market shape:
+  // 66.3 -> 60.1 us, issue slots 54 -> 64 % busy.  (Batches of 8 loads: same time for one warp per row, 80 registers
+  // and slower teams.)  Plain (L1-allocating) loads: the rare exact pass below re-reads a distance from L1.
+  bool have = i + 3 * S < nvec;
+  float4 a0, a1, a2, a3;
+  if (have) { a0 = __ldg(rv + i); a1 = __ldg(rv + i + S); a2 = __ldg(rv + i + 2 * S); a3 = __ldg(rv + i + 3 * S); }
+  while (have) {
+    const int in = i + 4 * S;
+    const bool more = in + 3 * S < nvec;
+    float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
+    if (more) { n0 = __ldg(rv + in); n1 = __ldg(rv + in + S); n2 = __ldg(rv + in + 2 * S); n3 = __ldg(rv + in + 3 * S); }
     uint32_t mask = 0;
     warp_visit8(c, a0, a1, mask);
     warp_visit8(c, a2, a3, mask);
@@ -487,6 +498,9 @@ __device__ __forceinline__ void warp_count_stream(WarpCount& c, int G, int lane,
       const int g = head + 4 * (i + (e >> 2) * S) + (e & 3);
       warp_fix(c, __ldg(row + g), (uint32_t)g);
     }
+    a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+    i = in;
+    have = more;
   }
   for (; i < nvec; i += S) {
     const int g0 = head + 4 * i;
