@@ -105,3 +105,26 @@ def test_signatures_match_the_reference():
     p = inspect.signature(re_ranking).parameters
     assert list(p) == ["q_g_dist", "q_q_dist", "g_g_dist", "k1", "k2", "lambda_value"]
     assert (p["k1"].default, p["k2"].default, p["lambda_value"].default) == (20, 6, 0.3)
+
+
+def test_shipped_library_is_tcgen05_tma_code_for_sm100a_only():
+    """The contraction kernels of the built .so are tcgen05 / TMEM / TMA code (UTCHMMA, LDTM, UTMALDG, UTMASTG in SASS),
+    there is no legacy mma.sync (HMMA / IMMA) anywhere, and sm_100a is the only architecture in the file."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _lib.load()
+    txt = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert set(re.findall(r"arch = (sm_\w+)", txt)) == {"sm_100a"}
+    ops_by_fn = {}
+    for m in re.finditer(r"Function : (\S+)\n(.*?)(?=\n\s*Function : |\Z)", txt, re.S):
+        ops_by_fn[m.group(1)] = set(re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", m.group(2), re.M))
+    gemm = {k: v for k, v in ops_by_fn.items() if "distmat_umma" in k}
+    assert len(gemm) >= 4
+    for name, ops in gemm.items():
+        assert {"UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"} <= ops, (name, sorted(ops))
+    assert any("UTMASTG" in ops for ops in gemm.values())
+    legacy = {k for k, ops in ops_by_fn.items() if ops & {"HMMA", "IMMA", "DMMA"}}
+    assert not legacy, legacy
