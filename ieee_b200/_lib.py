@@ -139,9 +139,16 @@ def check(code: int) -> None:
         raise IeeeB200Error(code, load().ieee_last_error().decode())
 
 
+_cuda_ok = False
+
+
 def require_cuda() -> None:
+    global _cuda_ok
+    if _cuda_ok:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("ieee_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _cuda_ok = True
 
 
 def ptr(t) -> int:

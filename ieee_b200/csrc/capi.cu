@@ -493,8 +493,7 @@ int ieee_gallery_prepare(const void* gf, int64_t ldg, int dtype, int64_t G, int6
   cudaStream_t stream = (cudaStream_t)stream_;
   IEEE_REQUIRE(gf && g_packed && G > 0 && D > 0, "gallery_prepare: bad arguments (G=%lld D=%lld)", (long long)G, (long long)D);
   const bool new_center = q != nullptr && !(flags & IEEE_PREPARE_KEEP_CENTER);
-  IEEE_REQUIRE(!new_center || (center != nullptr && workspace != nullptr && Q > 0),
-               "gallery_prepare: a centre from the query rows needs the centre buffer and the workspace");
+  IEEE_REQUIRE(!new_center || (center != nullptr && Q > 0), "gallery_prepare: a centre from the query rows needs the centre buffer");
   IEEE_REQUIRE(q_packed == nullptr || (q != nullptr && Q > 0), "gallery_prepare: packing the queries needs the query rows");
   tl_enter(stream, "enter gallery_prepare");
   SideLane* lane = nullptr;

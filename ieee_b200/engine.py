@@ -292,7 +292,6 @@ class RetrievalEvaluator:
             assert src.dtype == gf.dtype, "query and gallery features must have the same dtype"
         if src is not None and self._use_center and self.center is None:
             self.center = torch.empty(D, dtype=torch.float32, device=self.device)
-            ws = torch.empty(lib.ieee_gallery_prepare_workspace_bytes(D), dtype=torch.uint8, device=self.device)
         else:
             flags |= _lib.PREPARE_KEEP_CENTER
         center = self.center if self._use_center else None

@@ -53,7 +53,7 @@ class GalleryLabels:
         assert self.camids.numel() == self.G
         lib = _lib.load()
         self.group = torch.empty(lib.ieee_gallery_group_bytes(self.G), dtype=torch.uint8, device=device)
-        self._scratch = torch.empty(64, dtype=torch.int32, device=device)
+        self._scratch_buf = None   # (allocated on first use: only the capacity queries need it)
         self.ready = None
         self.side_join = False     # the grouping was left on the library's side stream (ieee_gallery_prepare, deferred join)
         if not build:
@@ -69,6 +69,12 @@ class GalleryLabels:
             else:
                 _lib.call("ieee_gallery_group", self.pids.data_ptr(), self.G, self.group.data_ptr(), cur.cuda_stream)
                 self.ready = cur.record_event()
+
+    @property
+    def _scratch(self) -> torch.Tensor:
+        if self._scratch_buf is None:
+            self._scratch_buf = torch.empty(64, dtype=torch.int32, device=self.pids.device)
+        return self._scratch_buf
 
     def wait(self, stream: torch.cuda.Stream, join: bool = True):
         """Order `stream` after the grouping.  join=False is for the one-call C entry points, which join the library's

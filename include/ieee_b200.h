@@ -256,8 +256,8 @@ int ieee_eval_market1501(const float* distmat, int64_t ld, int64_t Q, int64_t G,
  *   IEEE_PREPARE_DEFER_JOIN: the grouping is left running on the side stream; a stream must call
  *   ieee_gallery_group_join before it reads `group` (ieee_retrieve_eval_prepared* do that themselves, right before
  *   their gather stage: the label-only kernels then run beside the contraction instead of holding it up).
- * g_pids / group may be NULL to skip the grouping.  workspace: ieee_gallery_prepare_workspace_bytes(D) (only needed
- * when a centre is computed). */
+ * g_pids / group may be NULL to skip the grouping.  workspace: not used any more (the centre is one launch); may be
+ * NULL.  ieee_gallery_prepare_workspace_bytes is kept for callers that still size one. */
 #define IEEE_PREPARE_DEFER_JOIN 1
 #define IEEE_PREPARE_KEEP_CENTER 2
 size_t ieee_gallery_prepare_workspace_bytes(int64_t D);
