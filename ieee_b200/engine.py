@@ -373,6 +373,7 @@ class RetrievalEvaluator:
             if Q == 0:
                 return idx, val
             self._ensure_center(qf)
+            self._early_q = None          # (this path packs its query blocks itself: do not keep the early copy alive)
             if self._host_gallery is not None:
                 if self._copy is None:
                     self._copy = copy_stream(self.device)
