@@ -247,9 +247,27 @@ def eval_market1501(distmat, q_pids, g_pids, q_camids, g_camids, max_rank):
         cmc, summary = _evaluate_device_f64(d, q_pids, g_pids, q_camids, g_camids, max_rank)
         raise_for_status(summary, max_rank)
         return cmc.cpu().numpy(), float(summary.mAP)
-    cmc, summary, _ = evaluate_device(d, q_pids, g_pids, q_camids, g_camids, max_rank)
+    cmc, summary, st = evaluate_device(d, q_pids, g_pids, q_camids, g_camids, max_rank)
+    if summary.status == _lib.ERR_SHORT_RANK_LIST:
+        # rank.py:150,167: rows of cmc[:max_rank] stack into an array only when they are equally long -- i.e. when
+        # every valid query keeps the SAME number L < max_rank of gallery items; the reference then returns L ranks
+        L = _uniform_short_length(st, num_g)
+        if L is not None:
+            st.finalize(num_g, L)
+            cmc, summary = st.cmc, st.read_summary()
     raise_for_status(summary, max_rank)
     return cmc.cpu().numpy(), float(summary.mAP)
+
+
+def _uniform_short_length(st: "RankStages", num_g: int):
+    """The common kept-list length of all valid queries, or None when they differ (the last two columns of the count
+    rows hold the number of relevant and of junk gallery items per query)."""
+    c = st.counts.cpu().numpy()
+    n_rel, n_junk = c[:, -2], c[:, -1]
+    kept = num_g - n_junk[n_rel > 0]
+    if kept.size and int(kept.min()) == int(kept.max()) and int(kept[0]) >= 1:
+        return int(kept[0])
+    return None
 
 
 # The fork's own evaluate_rank(use_metric_cuhk03=True) dies with a TypeError (rank.py:236-239 hands 6 arguments to the

@@ -198,9 +198,18 @@ def test_max_rank_clamp_and_errors(capsys):
             evaluate_rank(empty, qp[:empty.shape[0]], gp[:empty.shape[1]], qc[:empty.shape[0]], gc[:empty.shape[1]])
     with pytest.raises(TypeError):                                                              # rank.py:236-239
         evaluate_rank(d, qp, gp, qc, gc, use_metric_cuhk03=True)
-    with pytest.raises(ValueError, match="fewer than max_rank"):     # all but 2 gallery items junk for query 0
-        gc2 = np.zeros(12, int); gp2 = np.zeros(12, int); gc2[:2] = 1
-        evaluate_rank(d, np.zeros(6, int), gp2, np.zeros(6, int), gc2, max_rank=5)
+    # kept lists shorter than max_rank (rank.py:150,167).  All but 2 gallery items are junk for camera-0 queries:
+    gc2 = np.zeros(12, int); gp2 = np.zeros(12, int); gc2[:2] = 1
+    # (a) EVERY valid query keeps the same 2 items: the reference stacks rows of length 2 and returns 2 ranks
+    cmc_u, map_u = evaluate_rank(d, np.zeros(6, int), gp2, np.zeros(6, int), gc2, max_rank=5)
+    cmc_r, map_r = ref.evaluate_rank(d, np.zeros(6, int), gp2, np.zeros(6, int), gc2, max_rank=5, use_cython=False)
+    assert cmc_u.shape == (2,) and np.array_equal(cmc_u, cmc_r) and abs(map_u - map_r) < 1e-9
+    # (b) lists of different length (camera-1 queries keep 10): the reference dies building a ragged array (ValueError)
+    qc2 = np.array([0, 1, 0, 1, 0, 1])
+    with pytest.raises(ValueError):
+        ref.evaluate_rank(d, np.zeros(6, int), gp2, qc2, gc2, max_rank=5, use_cython=False)
+    with pytest.raises(ValueError, match="fewer than max_rank"):
+        evaluate_rank(d, np.zeros(6, int), gp2, qc2, gc2, max_rank=5)
 
 
 def test_one_shot_c_entry_point():
